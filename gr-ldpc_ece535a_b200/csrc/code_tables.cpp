@@ -1,0 +1,209 @@
+// See code_tables.h.  Everything here is GF(2) on bit-packed rows: the reference does
+// the same steps on dense uBLAS int matrices (O(M^2 N) element operations and, in the
+// encoder, two dense real-valued LAPACK solves PER FRAME); here the factorisation runs
+// once per code and its effect is folded into one generator matrix P.
+#include "code_tables.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace ldpc535 {
+namespace {
+
+struct BitMat {
+    int rows = 0, cols = 0, words = 0;
+    std::vector<uint64_t> w;
+    BitMat() {}
+    BitMat(int r, int c) : rows(r), cols(c), words((c + 63) / 64), w((size_t)r * ((c + 63) / 64), 0) {}
+    uint64_t *row(int r) { return w.data() + (size_t)r * words; }
+    const uint64_t *row(int r) const { return w.data() + (size_t)r * words; }
+    bool get(int r, int c) const { return (row(r)[c >> 6] >> (c & 63)) & 1u; }
+    void set(int r, int c) { row(r)[c >> 6] |= (uint64_t)1 << (c & 63); }
+    void flip(int r, int c) { row(r)[c >> 6] ^= (uint64_t)1 << (c & 63); }
+};
+
+// first set bit of a row at column >= from, or -1
+int first_set_from(const uint64_t *r, int words, int from, int cols)
+{
+    int wi = from >> 6;
+    if (wi >= words) return -1;
+    uint64_t cur = r[wi] & (~(uint64_t)0 << (from & 63));
+    while (true) {
+        if (cur) {
+            int c = (wi << 6) + __builtin_ctzll(cur);
+            return c < cols ? c : -1;
+        }
+        if (++wi >= words) return -1;
+        cur = r[wi];
+    }
+}
+
+// call fn(c) for every set bit c of the row with lo <= c < hi
+template <class Fn>
+void for_each_set(const uint64_t *r, int lo, int hi, Fn fn)
+{
+    if (lo >= hi) return;
+    const int wlo = lo >> 6, whi = (hi - 1) >> 6;
+    for (int w = wlo; w <= whi; w++) {
+        uint64_t bits = r[w];
+        if (w == wlo) bits &= ~(uint64_t)0 << (lo & 63);
+        if (w == whi && (hi & 63)) bits &= ((uint64_t)1 << (hi & 63)) - 1;
+        while (bits) {
+            fn((w << 6) + __builtin_ctzll(bits));
+            bits &= bits - 1;
+        }
+    }
+}
+
+}  // namespace
+
+int build_code_tables(const int32_t *row_ptr_in, const int32_t *col_idx_in, int M, int N,
+                      CodeTables &t)
+{
+    if (!row_ptr_in || !col_idx_in || M < 1 || N <= M || N > 65535) return 1;
+    const int K = N - M;
+    const int E = row_ptr_in[M];
+    if (row_ptr_in[0] != 0 || E < 1) return 1;
+    for (int j = 0; j < M; j++) {
+        if (row_ptr_in[j + 1] < row_ptr_in[j]) return 1;
+        for (int e = row_ptr_in[j]; e < row_ptr_in[j + 1]; e++)
+            if (col_idx_in[e] < 0 || col_idx_in[e] >= N) return 1;
+    }
+
+    // F = H (original column order); it is column-swapped and row-reduced in place.
+    BitMat F(M, N);
+    for (int j = 0; j < M; j++)
+        for (int e = row_ptr_in[j]; e < row_ptr_in[j + 1]; e++) F.set(j, col_idx_in[e]);
+
+    t = CodeTables();
+    t.M = M; t.N = N; t.K = K;
+    t.pivots.assign(M, 0);
+    t.col_origin.resize(N);
+    for (int c = 0; c < N; c++) t.col_origin[c] = c;
+
+    // L (unit lower) and U (unit upper), M x M, as bit rows -- reorderHMatrix's outputs.
+    BitMat L(M, M), U(M, M);
+    bool singular = false;
+
+    for (int i = 0; i < M; i++) {
+        // 'First' strategy (lib/ldpc_decoder_cb_impl.cc:269-277): first non-zero of row i
+        // at or after the diagonal; the reference falls back to column 0 when there is none.
+        int chosen = first_set_from(F.row(i), F.words, i, N);
+        if (chosen < 0) { chosen = 0; singular = true; }
+        t.pivots[i] = chosen;
+
+        if (chosen != i) {   // swap columns i <-> chosen of F (and, by bookkeeping, of H) (:283-290)
+            for (int r = 0; r < M; r++) {
+                bool a = F.get(r, i), b = F.get(r, chosen);
+                if (a != b) { F.flip(r, i); F.flip(r, chosen); }
+            }
+            std::swap(t.col_origin[i], t.col_origin[chosen]);
+        }
+        // column i of F -> column i of L (rows >= i) and of U (rows <= i) (:293-294)
+        for (int r = i; r < M; r++) if (F.get(r, i)) L.set(r, i);
+        for (int r = 0; r <= i; r++) if (F.get(r, i)) U.set(r, i);
+        // add row i to every later row with a 1 in column i (:297-305).  Row i is zero
+        // left of the diagonal by now, so only words from i/64 on can change.
+        if (i < M - 1) {
+            const uint64_t *src = F.row(i);
+            const int w0 = i >> 6;
+            for (int k = i + 1; k < M; k++) {
+                if (F.get(k, i)) {
+                    uint64_t *dst = F.row(k);
+                    for (int w = w0; w < F.words; w++) dst[w] ^= src[w];
+                }
+            }
+        }
+    }
+    if (singular) return 4;
+    for (int i = 0; i < M; i++)
+        if (!L.get(i, i) || !U.get(i, i)) return 4;
+
+    // Re-ordered H: column c of H_perm is original column col_origin[c].
+    std::vector<int32_t> new_col(N);
+    for (int c = 0; c < N; c++) new_col[t.col_origin[c]] = c;
+    t.row_ptr.assign(row_ptr_in, row_ptr_in + M + 1);
+    t.col_idx.resize(E);
+    t.E = E;
+    for (int j = 0; j < M; j++) {
+        int a = t.row_ptr[j], b = t.row_ptr[j + 1];
+        for (int e = a; e < b; e++) t.col_idx[e] = new_col[col_idx_in[e]];
+        std::sort(t.col_idx.begin() + a, t.col_idx.begin() + b);
+        for (int e = a + 1; e < b; e++)
+            if (t.col_idx[e] == t.col_idx[e - 1]) return 1;     // duplicate entry
+    }
+    // CSC: edges of a column with rows ascending
+    t.col_ptr.assign(N + 1, 0);
+    for (int e = 0; e < E; e++) t.col_ptr[t.col_idx[e] + 1]++;
+    for (int c = 0; c < N; c++) t.col_ptr[c + 1] += t.col_ptr[c];
+    t.edge_of_col.resize(E);
+    {
+        std::vector<int32_t> fill(t.col_ptr.begin(), t.col_ptr.end() - 1);
+        for (int j = 0; j < M; j++)
+            for (int e = t.row_ptr[j]; e < t.row_ptr[j + 1]; e++) t.edge_of_col[fill[t.col_idx[e]]++] = e;
+    }
+
+    // Generator: c = U^-1 L^-1 (B d) with B = H_perm[:, M:N]
+    // (makeParityCheck, lib/ldpc_encoder_bc_impl.cc:275-294; the real-valued dgesv detour
+    // equals GF(2) substitution mod 2 -- DESIGN.md "Encoder semantics").
+    BitMat X(M, K);
+    for (int j = 0; j < M; j++)
+        for (int e = t.row_ptr[j]; e < t.row_ptr[j + 1]; e++)
+            if (t.col_idx[e] >= M) X.set(j, t.col_idx[e] - M);
+    for (int i = 0; i < M; i++) {                 // forward: X <- L^-1 X  (rows k < i are final)
+        uint64_t *xi = X.row(i);
+        for_each_set(L.row(i), 0, i, [&](int k) {
+            const uint64_t *xk = X.row(k);
+            for (int q = 0; q < X.words; q++) xi[q] ^= xk[q];
+        });
+    }
+    for (int i = M - 1; i >= 0; i--) {            // back: X <- U^-1 X  (rows k > i are final)
+        uint64_t *xi = X.row(i);
+        for_each_set(U.row(i), i + 1, M, [&](int k) {
+            const uint64_t *xk = X.row(k);
+            for (int q = 0; q < X.words; q++) xi[q] ^= xk[q];
+        });
+    }
+    t.kwords = (K + 31) / 32;
+    t.mwords = (M + 31) / 32;
+    t.P.assign((size_t)M * t.kwords, 0);
+    t.Pt.assign((size_t)K * t.mwords, 0);
+    for (int j = 0; j < M; j++)
+        for (int k = 0; k < K; k++)
+            if (X.get(j, k)) {
+                t.P[(size_t)j * t.kwords + (k >> 5)] |= 1u << (k & 31);
+                t.Pt[(size_t)k * t.mwords + (j >> 5)] |= 1u << (j & 31);
+            }
+
+    // Decoder tables (slot-major message layout).
+    t.chk_deg.assign(M, 0);
+    t.var_deg.assign(N, 0);
+    for (int j = 0; j < M; j++) {
+        int d = t.row_ptr[j + 1] - t.row_ptr[j];
+        if (d > 255) return 1;
+        t.chk_deg[j] = (uint8_t)d;
+        t.dc_max = std::max(t.dc_max, d);
+    }
+    for (int c = 0; c < N; c++) {
+        int d = t.col_ptr[c + 1] - t.col_ptr[c];
+        if (d > 255) return 1;
+        t.var_deg[c] = (uint8_t)d;
+        t.dv_max = std::max(t.dv_max, d);
+    }
+    t.edge_slot.resize(E);
+    if ((size_t)t.dc_max * M <= 65535) {
+        t.chk_var.assign((size_t)t.dc_max * M, 0xFFFF);
+        t.var_slot.assign((size_t)t.dv_max * N, 0xFFFF);
+        for (int j = 0; j < M; j++)
+            for (int e = t.row_ptr[j], s = 0; e < t.row_ptr[j + 1]; e++, s++) {
+                t.chk_var[(size_t)s * M + j] = (uint16_t)t.col_idx[e];
+                t.edge_slot[e] = s * M + j;
+            }
+        for (int c = 0; c < N; c++)
+            for (int q = t.col_ptr[c], k = 0; q < t.col_ptr[c + 1]; q++, k++)
+                t.var_slot[(size_t)k * N + c] = (uint16_t)t.edge_slot[t.edge_of_col[q]];
+    }
+    return 0;
+}
+
+}  // namespace ldpc535

@@ -1,0 +1,43 @@
+// Host-side, one-time code setup: the reference constructors' reorderHMatrix
+// (lib/ldpc_decoder_cb_impl.cc:255-307 == lib/ldpc_encoder_bc_impl.cc:225-273) done on
+// bit-packed rows, the encoder's generator P = (L U)^-1 B over GF(2), and the
+// adjacency tables the decoder kernels read.  Plain C++, no CUDA.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace ldpc535 {
+
+struct CodeTables {
+    int M = 0, N = 0, K = 0, E = 0;
+    int dc_max = 0, dv_max = 0;
+
+    std::vector<int32_t> pivots;        // [M]   chosenCol of every re-ordering step
+    std::vector<int32_t> col_origin;    // [N]   re-ordered column c holds original column col_origin[c]
+
+    // re-ordered H
+    std::vector<int32_t> row_ptr;       // [M+1]
+    std::vector<int32_t> col_idx;       // [E]   columns ascending within a row (CSR edge order)
+    std::vector<int32_t> col_ptr;       // [N+1]
+    std::vector<int32_t> edge_of_col;   // [E]   CSR edge ids of a column, rows ascending
+
+    // encoder: parity c_j = <P_j, d> mod 2
+    int kwords = 0;                     // (K + 31) / 32
+    std::vector<uint32_t> P;            // [M][kwords]  row-major, bit k of row j = P(j,k)
+    std::vector<uint32_t> Pt;           // [K][mwords]  transposed: bit j of row k = P(j,k)
+    int mwords = 0;                     // (M + 31) / 32
+
+    // decoder: messages live slot-major, index s * M + j = slot s of check j
+    std::vector<uint16_t> chk_var;      // [dc_max][M]  variable of (slot, check) or 0xFFFF
+    std::vector<uint16_t> var_slot;     // [dv_max][N]  message index of the k-th check of a
+                                        //              variable (checks ascending) or 0xFFFF
+    std::vector<uint8_t> chk_deg;       // [M]
+    std::vector<uint8_t> var_deg;       // [N]
+    std::vector<int32_t> edge_slot;     // [E]  CSR edge id -> message index (message dumps)
+};
+
+// status: 0 ok, 1 invalid input, 4 singular (no pivot on some row)  (== LDPC535_* codes)
+int build_code_tables(const int32_t *row_ptr, const int32_t *col_idx, int M, int N,
+                      CodeTables &out);
+
+}  // namespace ldpc535

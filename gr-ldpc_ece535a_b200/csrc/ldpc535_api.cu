@@ -1,0 +1,748 @@
+// C ABI of the B200 LDPC hot path (include/ldpc535.h): handle management, table upload,
+// kernel dispatch, and the pinned-buffer H2D -> kernel -> D2H pipeline behind the
+// host-buffer entry points.  No CPU fallback anywhere: without a usable sm_100 device
+// every compute entry point returns an error.
+#include "../../include/ldpc535.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "code_tables.h"
+#include "decode_kernels.cuh"
+#include "decode_c4_kernel.cuh"
+#include "encode_kernels.cuh"
+#include "ldpc535_default_code.h"
+
+using namespace ldpc535;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string &msg)
+{
+    g_last_error = msg;
+    return status;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(LDPC535_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3 };
+
+constexpr int kSlots = 3;                       // pipeline depth of the host-buffer API
+constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void *d_sym = nullptr;        // kChunkSymBytes
+    long long *d_off = nullptr;   // max windows
+    signed char *d_pol = nullptr;
+    uint8_t *d_bytes = nullptr, *d_synd = nullptr, *d_iters = nullptr;
+    long long *h_off = nullptr;   // pinned, rebased offsets
+};
+
+}  // namespace
+
+struct ldpc535_code {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    CodeTables t;
+    // device tables
+    uint16_t *d_chk_var = nullptr, *d_var_slot = nullptr;
+    uint8_t *d_chk_deg = nullptr;
+    int32_t *d_slot_edge = nullptr;
+    uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
+    int tabA_bytes = 0, tabB_bytes = 0;
+    int dc_t = 0, dv_t = 0;           // template sizes used (6/3 or 16/8), 0 = unsupported degrees
+    bool fits_warp = false, fits_block = false, is_c4 = false;
+    int stage_tables = 0;
+    size_t block_smem = 0;
+    int block_threads = 0;
+    int forced = kAuto;
+    cudaStream_t stream = nullptr;
+    // host-API pipeline
+    bool slots_ready = false;
+    size_t max_win_per_chunk = 0;
+    Slot slots[kSlots];
+    uint64_t launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (dev < 0) { ok = false; return; }
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define NEED_DEVICE(c, g)                                                                  \
+    do {                                                                                   \
+        if ((c)->device < 0)                                                               \
+            return fail(LDPC535_ERR_NO_DEVICE, "handle was created with LDPC535_DEVICE_NONE (tables only; there is no CPU compute path)"); \
+        if (!(g).ok) return fail(LDPC535_ERR_CUDA, "cudaSetDevice failed");                \
+    } while (0)
+
+template <typename T>
+int upload(T **dptr, const void *src, size_t bytes, size_t alloc_bytes)
+{
+    CU(cudaMalloc(reinterpret_cast<void **>(dptr), alloc_bytes));
+    CU(cudaMemset(*dptr, 0xFF, alloc_bytes));
+    CU(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+    return LDPC535_OK;
+}
+
+bool tables_match_c4(const CodeTables &t);
+
+int finish_create(ldpc535_code *c)
+{
+    const CodeTables &t = c->t;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10)
+        return fail(LDPC535_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) +
+                                               std::to_string(prop.minor) + ", kernels are built for sm_100a");
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    if (t.dc_max <= 6 && t.dv_max <= 3) { c->dc_t = 6; c->dv_t = 3; }
+    else if (t.dc_max <= 16 && t.dv_max <= 8) { c->dc_t = 16; c->dv_t = 8; }
+    else return fail(LDPC535_ERR_UNSUPPORTED, "check degree > 16 or bit degree > 8");
+    if (t.chk_var.empty())
+        return fail(LDPC535_ERR_UNSUPPORTED, "dc_max * M exceeds 65535 message slots");
+
+    // decoder tables, padded to the template slot counts (extra slots = 0xFFFF)
+    const size_t a_bytes = (size_t)c->dc_t * t.M * sizeof(uint16_t);
+    const size_t b_bytes = (size_t)c->dv_t * t.N * sizeof(uint16_t);
+    c->tabA_bytes = (int)((a_bytes + 15) & ~(size_t)15);
+    c->tabB_bytes = (int)((b_bytes + 15) & ~(size_t)15);
+    int st;
+    if ((st = upload(&c->d_chk_var, t.chk_var.data(), t.chk_var.size() * 2, c->tabA_bytes))) return st;
+    if ((st = upload(&c->d_var_slot, t.var_slot.data(), t.var_slot.size() * 2, c->tabB_bytes))) return st;
+    if ((st = upload(&c->d_chk_deg, t.chk_deg.data(), t.chk_deg.size(), t.chk_deg.size()))) return st;
+    {
+        std::vector<int32_t> slot_edge((size_t)c->dc_t * t.M, -1);
+        for (int e = 0; e < t.E; e++) slot_edge[t.edge_slot[e]] = e;
+        if ((st = upload(&c->d_slot_edge, slot_edge.data(), slot_edge.size() * 4, slot_edge.size() * 4))) return st;
+    }
+    // encoder tables
+    if ((st = upload(&c->d_Pt, t.Pt.data(), t.Pt.size() * 4, std::max<size_t>(t.Pt.size() * 4, 128)))) return st;
+    {
+        std::vector<uint32_t> Pw((size_t)t.kwords * t.M);
+        for (int j = 0; j < t.M; j++)
+            for (int w = 0; w < t.kwords; w++) Pw[(size_t)w * t.M + j] = t.P[(size_t)j * t.kwords + w];
+        if ((st = upload(&c->d_Pw, Pw.data(), Pw.size() * 4, Pw.size() * 4))) return st;
+    }
+
+    c->fits_warp = (t.M <= 32 && t.N <= 64);
+    c->is_c4 = tables_match_c4(t);
+    const size_t fixed = block_smem_fixed_bytes(c->dc_t, t.M, t.N);
+    const size_t staged = fixed + c->tabA_bytes + c->tabB_bytes;
+    if (staged <= c->smem_optin) { c->stage_tables = 1; c->block_smem = staged; c->fits_block = true; }
+    else if (fixed <= c->smem_optin) { c->stage_tables = 0; c->block_smem = fixed; c->fits_block = true; }
+    int nt = std::max(t.M, (t.N + 1) / 2);
+    nt = std::min(1024, ((nt + 31) / 32) * 32);
+    c->block_threads = std::max(nt, 64);
+    if (!c->fits_warp && !c->fits_block)
+        return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the shared-memory resident decoder");
+    return LDPC535_OK;
+}
+
+void release(ldpc535_code *c)
+{
+    if (!c) return;
+    if (c->device < 0) { delete c; return; }
+    DeviceGuard g(c->device);
+    for (auto &s : c->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_sym); cudaFree(s.d_off); cudaFree(s.d_pol);
+        cudaFree(s.d_bytes); cudaFree(s.d_synd); cudaFree(s.d_iters);
+        if (s.h_off) cudaFreeHost(s.h_off);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw);
+    delete c;
+}
+
+int family_from_name(const char *name, int *out)
+{
+    if (!name || !*name || !strcmp(name, "auto")) { *out = kAuto; return 0; }
+    if (!strcmp(name, "warp")) { *out = kWarp; return 0; }
+    if (!strcmp(name, "block")) { *out = kBlock; return 0; }
+    if (!strcmp(name, "c4-thread")) { *out = kC4Thread; return 0; }
+    return 1;
+}
+
+int resolve_family(const ldpc535_code *c, int forced, int method)
+{
+    int f = forced;
+    if (f == kAuto) {
+        if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT) f = kC4Thread;
+        else if (c->fits_warp) f = kWarp;
+        else f = kBlock;
+    }
+    if (f == kC4Thread && !(c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
+    if (f == kWarp && !c->fits_warp) return -1;
+    if (f == kBlock && !c->fits_block) return -1;
+    return f;
+}
+
+int norm_method(int method) { return (method >= 1 && method <= 3) ? method : 0; }
+
+// ---- launches --------------------------------------------------------------------
+
+template <int METHOD, int DC, int DV, bool DBG>
+cudaError_t launch_warp(const ldpc535_code *c, const DecodeParams &p, cudaStream_t st)
+{
+    const int wpb = kWarpKernelThreads / 32;
+    const size_t smem = sizeof(float) * wpb * DC * 32;
+    long long blocks = (p.n_win + wpb - 1) / wpb;
+    const int grid = (int)std::min<long long>(blocks, (long long)c->sm_count * 16);
+    decode_warp_kernel<METHOD, DC, DV, DBG><<<grid, kWarpKernelThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int METHOD, int DC, int DV, bool DBG>
+cudaError_t launch_block(const ldpc535_code *c, const DecodeParams &p, cudaStream_t st)
+{
+    auto kern = decode_block_kernel<METHOD, DC, DV, DBG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->block_smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, c->block_threads, c->block_smem);
+    if (e != cudaSuccess) return e;
+    per_sm = std::max(per_sm, 1);
+    const int grid = (int)std::min<long long>(p.n_win, (long long)c->sm_count * per_sm);
+    kern<<<grid, c->block_threads, c->block_smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int DC, int DV>
+cudaError_t launch_generic(const ldpc535_code *c, int family, int method, bool dbg,
+                           const DecodeParams &p, cudaStream_t st)
+{
+    if (family == kWarp) {
+        if (dbg) return launch_warp<kMethodSpa, DC, DV, true>(c, p, st);
+        switch (method) {
+        case 1: return launch_warp<kMethodSpa, DC, DV, false>(c, p, st);
+        case 2: return launch_warp<kMethodBitFlip, DC, DV, false>(c, p, st);
+        case 3: return launch_warp<kMethodHard, DC, DV, false>(c, p, st);
+        default: return launch_warp<kMethodMinSum, DC, DV, false>(c, p, st);
+        }
+    }
+    if (dbg) return launch_block<kMethodSpa, DC, DV, true>(c, p, st);
+    switch (method) {
+    case 1: return launch_block<kMethodSpa, DC, DV, false>(c, p, st);
+    case 2: return launch_block<kMethodBitFlip, DC, DV, false>(c, p, st);
+    case 3: return launch_block<kMethodHard, DC, DV, false>(c, p, st);
+    default: return launch_block<kMethodMinSum, DC, DV, false>(c, p, st);
+    }
+}
+
+int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParams p, cudaStream_t st)
+{
+    method = norm_method(method);
+    const int family = resolve_family(c, forced, method);
+    if (family < 0) return fail(LDPC535_ERR_UNSUPPORTED, "kernel family not available for this code/method");
+    if (p.n_win == 0) return LDPC535_OK;
+    p.M = c->t.M; p.N = c->t.N; p.K = c->t.K; p.E = c->t.E;
+    p.nbytes = (c->t.K + 7) / 8;
+    p.chk_var = c->d_chk_var; p.var_slot = c->d_var_slot; p.chk_deg = c->d_chk_deg;
+    p.slot_edge = c->d_slot_edge;
+    p.stage_tables = c->stage_tables; p.tabA_bytes = c->tabA_bytes; p.tabB_bytes = c->tabB_bytes;
+    cudaError_t e;
+    if (family == kC4Thread) e = launch_c4_thread(p, dbg, c->sm_count, st);
+    else if (c->dc_t == 6) e = launch_generic<6, 3>(c, family, method, dbg, p, st);
+    else e = launch_generic<16, 8>(c, family, method, dbg, p, st);
+    if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("decode launch: ") + cudaGetErrorString(e));
+    c->launches++;
+    return LDPC535_OK;
+}
+
+int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *d_out, cudaStream_t st)
+{
+    if (n_frames == 0) return LDPC535_OK;
+    const CodeTables &t = c->t;
+    EncodeParams p;
+    p.in = d_in; p.n_frames = (long long)n_frames; p.out = reinterpret_cast<float2 *>(d_out);
+    p.M = t.M; p.N = t.N; p.K = t.K; p.nbytes = (t.K + 7) / 8; p.kwords = t.kwords; p.mwords = t.mwords;
+    p.Pt = c->d_Pt; p.Pw = c->d_Pw;
+    if (t.M <= 32 && t.K <= 32) {
+        const long long warps = ((long long)n_frames + 31) / 32;
+        const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)c->sm_count * 8);
+        encode_small_kernel<<<grid, 256, 0, st>>>(p);
+    } else {
+        const size_t smem = encode_generic_smem_bytes(t.kwords, t.mwords);
+        if (smem > c->smem_optin) return fail(LDPC535_ERR_UNSUPPORTED, "code too large for the encoder tile");
+        cudaError_t e = cudaFuncSetAttribute(encode_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
+        const long long tiles = ((long long)n_frames + kEncTile - 1) / kEncTile;
+        const int grid = (int)std::min<long long>(tiles, (long long)c->sm_count * 4);
+        encode_generic_kernel<<<grid, kEncThreads, smem, st>>>(p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("encode launch: ") + cudaGetErrorString(e));
+    c->launches++;
+    return LDPC535_OK;
+}
+
+int ensure_slots(ldpc535_code *c)
+{
+    if (c->slots_ready) return LDPC535_OK;
+    const size_t frame_bytes = (size_t)c->t.N * 8;
+    c->max_win_per_chunk = std::max<size_t>(1, kChunkSymBytes / frame_bytes);
+    const size_t nb = (size_t)(c->t.K + 7) / 8;
+    for (auto &s : c->slots) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CU(cudaMalloc(&s.d_sym, std::max(kChunkSymBytes, frame_bytes)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_off), c->max_win_per_chunk * sizeof(long long)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_pol), c->max_win_per_chunk));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_bytes), c->max_win_per_chunk * nb));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_synd), c->max_win_per_chunk));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_iters), c->max_win_per_chunk));
+        CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_off), c->max_win_per_chunk * sizeof(long long)));
+    }
+    c->slots_ready = true;
+    return LDPC535_OK;
+}
+
+int create_common(const int32_t *row_ptr, const int32_t *col_idx, int M, int N, int device,
+                  ldpc535_code **out)
+{
+    if (!out) return fail(LDPC535_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (device != LDPC535_DEVICE_NONE) {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            return fail(LDPC535_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+        }
+        if (device < 0 || device >= count) return fail(LDPC535_ERR_NO_DEVICE, "device index out of range");
+    }
+    ldpc535_code *c = new (std::nothrow) ldpc535_code();
+    if (!c) return fail(LDPC535_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    int st = build_code_tables(row_ptr, col_idx, M, N, c->t);
+    if (st) {
+        delete c;
+        return fail(st, st == LDPC535_ERR_SINGULAR ? "reorderHMatrix: a row has no pivot (singular L/U)"
+                                                   : "invalid parity-check matrix");
+    }
+    if (device == LDPC535_DEVICE_NONE) {     // tables only: introspection works, compute refuses
+        *out = c;
+        return LDPC535_OK;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) { delete c; return fail(LDPC535_ERR_CUDA, "cudaSetDevice failed"); }
+    st = finish_create(c);
+    if (st) { release(c); return st; }
+    *out = c;
+    return LDPC535_OK;
+}
+
+}  // namespace
+
+// ===================================================================================
+extern "C" {
+
+const char *ldpc535_version(void) { return "ldpc535 0.1 (sm_100a)"; }
+
+const char *ldpc535_strerror(int status)
+{
+    switch (status) {
+    case LDPC535_OK: return "ok";
+    case LDPC535_ERR_INVALID: return "invalid argument";
+    case LDPC535_ERR_NO_DEVICE: return "no usable CUDA device";
+    case LDPC535_ERR_CUDA: return "CUDA error";
+    case LDPC535_ERR_SINGULAR: return "parity-check matrix has no LU pivot order (singular)";
+    case LDPC535_ERR_UNSUPPORTED: return "unsupported code or kernel";
+    case LDPC535_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+const char *ldpc535_last_error(void) { return g_last_error.c_str(); }
+
+int ldpc535_device_count(int *count)
+{
+    if (!count) return fail(LDPC535_ERR_INVALID, "count is NULL");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return LDPC535_OK;
+}
+
+int ldpc535_device_info(int device, char *name, int *sm_major, int *sm_minor, int *sm_count,
+                        int *sm_clock_khz)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        return fail(LDPC535_ERR_NO_DEVICE, "no such device");
+    }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (name) { strncpy(name, prop.name, 127); name[127] = 0; }
+    if (sm_major) *sm_major = prop.major;
+    if (sm_minor) *sm_minor = prop.minor;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (sm_clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *sm_clock_khz = khz;
+    }
+    return LDPC535_OK;
+}
+
+int ldpc535_code_create_sparse(const int32_t *row_ptr, const int32_t *col_idx, int M, int N,
+                               int device, ldpc535_code **out)
+{
+    return create_common(row_ptr, col_idx, M, N, device, out);
+}
+
+int ldpc535_code_create(const int32_t *H, int M, int N, int device, ldpc535_code **out)
+{
+    if (!H || M < 1 || N < 1) return fail(LDPC535_ERR_INVALID, "bad H");
+    std::vector<int32_t> row_ptr(M + 1, 0), col_idx;
+    for (int j = 0; j < M; j++) {
+        for (int i = 0; i < N; i++)
+            if (H[(size_t)j * N + i] != 0) col_idx.push_back(i);
+        row_ptr[j + 1] = (int32_t)col_idx.size();
+    }
+    return create_common(row_ptr.data(), col_idx.data(), M, N, device, out);
+}
+
+int ldpc535_code_create_default(int device, ldpc535_code **out)
+{
+    return create_common(ldpc535_default_row_ptr, ldpc535_default_col_idx, LDPC535_DEFAULT_M,
+                         LDPC535_DEFAULT_N, device, out);
+}
+
+void ldpc535_code_destroy(ldpc535_code *code) { release(code); }
+
+int ldpc535_code_info(const ldpc535_code *c, int *M, int *N, int *K, int *E, int *device)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    if (M) *M = c->t.M;
+    if (N) *N = c->t.N;
+    if (K) *K = c->t.K;
+    if (E) *E = c->t.E;
+    if (device) *device = c->device;
+    return LDPC535_OK;
+}
+
+int ldpc535_code_get_pivots(const ldpc535_code *c, int32_t *chosen)
+{
+    if (!c || !chosen) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    memcpy(chosen, c->t.pivots.data(), sizeof(int32_t) * c->t.M);
+    return LDPC535_OK;
+}
+
+int ldpc535_code_get_h(const ldpc535_code *c, int32_t *row_ptr, int32_t *col_idx)
+{
+    if (!c || !row_ptr || !col_idx) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    memcpy(row_ptr, c->t.row_ptr.data(), sizeof(int32_t) * (c->t.M + 1));
+    memcpy(col_idx, c->t.col_idx.data(), sizeof(int32_t) * c->t.E);
+    return LDPC535_OK;
+}
+
+int ldpc535_code_get_generator(const ldpc535_code *c, uint32_t *P)
+{
+    if (!c || !P) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    memcpy(P, c->t.P.data(), sizeof(uint32_t) * c->t.P.size());
+    return LDPC535_OK;
+}
+
+const char *ldpc535_code_kernel_name(const ldpc535_code *c, int method)
+{
+    if (!c) return "";
+    switch (resolve_family(c, c->forced, norm_method(method))) {
+    case kWarp: return "warp";
+    case kBlock: return "block";
+    case kC4Thread: return "c4-thread";
+    default: return "unsupported";
+    }
+}
+
+int ldpc535_code_set_kernel(ldpc535_code *c, const char *kernel)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    int f;
+    if (family_from_name(kernel, &f)) return fail(LDPC535_ERR_INVALID, "unknown kernel family");
+    if (f == kWarp && !c->fits_warp) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the warp kernel");
+    if (f == kBlock && !c->fits_block) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the block kernel");
+    if (f == kC4Thread && !c->is_c4) return fail(LDPC535_ERR_UNSUPPORTED, "not the shipped 32x64 code");
+    c->forced = f;
+    return LDPC535_OK;
+}
+
+uint64_t ldpc535_launch_count(const ldpc535_code *c) { return c ? c->launches : 0; }
+
+int ldpc535_host_alloc(size_t bytes, void **ptr)
+{
+    if (!ptr) return fail(LDPC535_ERR_INVALID, "ptr is NULL");
+    CU(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return LDPC535_OK;
+}
+
+int ldpc535_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return LDPC535_OK;
+}
+
+int ldpc535_dev_alloc(ldpc535_code *c, size_t bytes, void **dptr)
+{
+    if (!c || !dptr) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    CU(cudaMalloc(dptr, bytes ? bytes : 1));
+    return LDPC535_OK;
+}
+
+int ldpc535_dev_free(ldpc535_code *c, void *dptr)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    if (dptr) CU(cudaFree(dptr));
+    return LDPC535_OK;
+}
+
+int ldpc535_memcpy_h2d(ldpc535_code *c, void *dptr, const void *hptr, size_t bytes)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    CU(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return LDPC535_OK;
+}
+
+int ldpc535_memcpy_d2h(ldpc535_code *c, void *hptr, const void *dptr, size_t bytes)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    CU(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return LDPC535_OK;
+}
+
+int ldpc535_stream_sync(ldpc535_code *c, void *stream)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    CU(cudaStreamSynchronize(stream ? (cudaStream_t)stream : c->stream));
+    return LDPC535_OK;
+}
+
+int ldpc535_encode_batch_dev(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *d_out,
+                             void *stream)
+{
+    if (!c || (n_frames && (!d_in || !d_out))) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    return launch_encode(c, d_in, n_frames, d_out, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int ldpc535_decode_batch_dev(ldpc535_code *c, const float *d_sym, size_t n_sym,
+                             const int64_t *d_win_offset, const int8_t *d_polarity, size_t n_win,
+                             int method, int max_iters, int early_stop, int synd_threshold,
+                             uint8_t *d_out_bytes, uint8_t *d_out_synd, uint8_t *d_out_iters,
+                             void *stream)
+{
+    if (!c || (n_win && (!d_sym || !d_out_bytes))) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    if (max_iters < 1 || max_iters > 255) return fail(LDPC535_ERR_INVALID, "max_iters must be 1..255");
+    if (synd_threshold < 0) return fail(LDPC535_ERR_INVALID, "synd_threshold < 0");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    DecodeParams p = {};
+    p.sym = reinterpret_cast<const float2 *>(d_sym);
+    p.n_sym = (long long)n_sym;
+    p.win_offset = reinterpret_cast<const long long *>(d_win_offset);
+    p.polarity = reinterpret_cast<const signed char *>(d_polarity);
+    p.n_win = (long long)n_win;
+    p.max_iters = max_iters; p.early_stop = early_stop ? 1 : 0; p.thr = std::min(synd_threshold, 253);
+    p.out_bytes = d_out_bytes; p.out_synd = d_out_synd; p.out_iters = d_out_iters;
+    return launch_decode(c, c->forced, method, false, p, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int ldpc535_encode_batch(ldpc535_code *c, const uint8_t *in, size_t n_frames, float *out)
+{
+    if (!c || (n_frames && (!in || !out))) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    int st = ensure_slots(c);
+    if (st) return st;
+    const size_t nb = (size_t)(c->t.K + 7) / 8;
+    const size_t frame_bytes = (size_t)c->t.N * 8;
+    // the symbol staging buffer holds the OUTPUT here; input bytes ride in d_bytes
+    const size_t chunk = c->max_win_per_chunk;
+    size_t done = 0;
+    int k = 0;
+    while (done < n_frames) {
+        Slot &s = c->slots[k % kSlots];
+        const size_t n = std::min(chunk, n_frames - done);
+        CU(cudaStreamSynchronize(s.stream));
+        CU(cudaMemcpyAsync(s.d_bytes, in + done * nb, n * nb, cudaMemcpyHostToDevice, s.stream));
+        st = launch_encode(c, s.d_bytes, n, reinterpret_cast<float *>(s.d_sym), s.stream);
+        if (st) return st;
+        CU(cudaMemcpyAsync(out + done * c->t.N * 2, s.d_sym, n * frame_bytes, cudaMemcpyDeviceToHost, s.stream));
+        done += n;
+        k++;
+    }
+    for (auto &s : c->slots) CU(cudaStreamSynchronize(s.stream));
+    return LDPC535_OK;
+}
+
+int ldpc535_decode_batch(ldpc535_code *c, const float *sym, size_t n_sym, const int64_t *win_offset,
+                         const int8_t *polarity, size_t n_win, int method, int max_iters,
+                         int early_stop, int synd_threshold, uint8_t *out_bytes, uint8_t *out_synd,
+                         uint8_t *out_iters)
+{
+    if (!c || (n_win && (!sym || !out_bytes))) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    if (max_iters < 1 || max_iters > 255) return fail(LDPC535_ERR_INVALID, "max_iters must be 1..255");
+    if (synd_threshold < 0) return fail(LDPC535_ERR_INVALID, "synd_threshold < 0");
+    const size_t N = (size_t)c->t.N;
+    const size_t nb = (size_t)(c->t.K + 7) / 8;
+    if (!win_offset) {
+        if (n_win * N > n_sym) return fail(LDPC535_ERR_INVALID, "n_win * N exceeds n_sym");
+    } else {
+        for (size_t w = 0; w < n_win; w++)
+            if (win_offset[w] < 0 || (size_t)win_offset[w] + N > n_sym)
+                return fail(LDPC535_ERR_INVALID, "window offset out of range");
+    }
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    int st = ensure_slots(c);
+    if (st) return st;
+    const size_t max_sym = kChunkSymBytes / 8;     // symbols per staging buffer
+    size_t done = 0;
+    int k = 0;
+    while (done < n_win) {
+        Slot &s = c->slots[k % kSlots];
+        CU(cudaStreamSynchronize(s.stream));
+        size_t n = 0, sym_lo = 0, sym_hi = 0;
+        if (!win_offset) {
+            n = std::min(c->max_win_per_chunk, n_win - done);
+            sym_lo = done * N;
+            sym_hi = sym_lo + n * N;
+        } else {
+            // grow the chunk while the span of symbols it touches fits the staging buffer
+            size_t lo = (size_t)win_offset[done], hi = lo + N;
+            n = 1;
+            while (done + n < n_win && n < c->max_win_per_chunk) {
+                const size_t o = (size_t)win_offset[done + n];
+                const size_t nlo = std::min(lo, o), nhi = std::max(hi, o + N);
+                if (nhi - nlo > max_sym) break;
+                lo = nlo; hi = nhi; n++;
+            }
+            sym_lo = lo; sym_hi = hi;
+            for (size_t i = 0; i < n; i++) s.h_off[i] = (long long)((size_t)win_offset[done + i] - lo);
+            CU(cudaMemcpyAsync(s.d_off, s.h_off, n * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+        }
+        CU(cudaMemcpyAsync(s.d_sym, sym + sym_lo * 2, (sym_hi - sym_lo) * 8, cudaMemcpyHostToDevice, s.stream));
+        if (polarity)
+            CU(cudaMemcpyAsync(s.d_pol, polarity + done, n, cudaMemcpyHostToDevice, s.stream));
+        DecodeParams p = {};
+        p.sym = reinterpret_cast<const float2 *>(s.d_sym);
+        p.n_sym = (long long)(sym_hi - sym_lo);
+        p.win_offset = win_offset ? s.d_off : nullptr;
+        p.polarity = polarity ? s.d_pol : nullptr;
+        p.n_win = (long long)n;
+        p.max_iters = max_iters; p.early_stop = early_stop ? 1 : 0; p.thr = std::min(synd_threshold, 253);
+        p.out_bytes = s.d_bytes; p.out_synd = s.d_synd; p.out_iters = s.d_iters;
+        st = launch_decode(c, c->forced, method, false, p, s.stream);
+        if (st) return st;
+        CU(cudaMemcpyAsync(out_bytes + done * nb, s.d_bytes, n * nb, cudaMemcpyDeviceToHost, s.stream));
+        if (out_synd) CU(cudaMemcpyAsync(out_synd + done, s.d_synd, n, cudaMemcpyDeviceToHost, s.stream));
+        if (out_iters) CU(cudaMemcpyAsync(out_iters + done, s.d_iters, n, cudaMemcpyDeviceToHost, s.stream));
+        done += n;
+        k++;
+    }
+    for (auto &s : c->slots) CU(cudaStreamSynchronize(s.stream));
+    return LDPC535_OK;
+}
+
+int ldpc535_decode_debug(ldpc535_code *c, const float *sym, size_t n_win, int max_iters,
+                         int early_stop, const char *kernel, float *out_L, float *out_E,
+                         float *out_M, uint8_t *out_bytes, uint8_t *out_iters)
+{
+    if (!c || !sym) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    if (max_iters < 1 || max_iters > 255) return fail(LDPC535_ERR_INVALID, "max_iters must be 1..255");
+    int fam;
+    if (family_from_name(kernel, &fam)) return fail(LDPC535_ERR_INVALID, "unknown kernel family");
+    if (fam == kAuto) fam = c->forced;
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    const size_t N = (size_t)c->t.N, E = (size_t)c->t.E, nb = (size_t)(c->t.K + 7) / 8;
+    float *d_sym = nullptr, *dL = nullptr, *dE = nullptr, *dM = nullptr;
+    uint8_t *d_bytes = nullptr, *d_iters = nullptr;
+    int st = LDPC535_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_sym); cudaFree(dL); cudaFree(dE); cudaFree(dM); cudaFree(d_bytes); cudaFree(d_iters);
+    };
+#define CUX(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            cleanup();                                                                     \
+            return fail(LDPC535_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+        }                                                                                  \
+    } while (0)
+    CUX(cudaMalloc(reinterpret_cast<void **>(&d_sym), std::max<size_t>(n_win * N * 8, 8)));
+    CUX(cudaMalloc(reinterpret_cast<void **>(&dL), std::max<size_t>(n_win * N * 4, 4)));
+    CUX(cudaMalloc(reinterpret_cast<void **>(&dE), std::max<size_t>(n_win * E * 4, 4)));
+    CUX(cudaMalloc(reinterpret_cast<void **>(&dM), std::max<size_t>(n_win * E * 4, 4)));
+    CUX(cudaMalloc(reinterpret_cast<void **>(&d_bytes), std::max<size_t>(n_win * nb, 1)));
+    CUX(cudaMalloc(reinterpret_cast<void **>(&d_iters), std::max<size_t>(n_win, 1)));
+    CUX(cudaMemcpyAsync(d_sym, sym, n_win * N * 8, cudaMemcpyHostToDevice, c->stream));
+    CUX(cudaMemsetAsync(dL, 0, std::max<size_t>(n_win * N * 4, 4), c->stream));
+    CUX(cudaMemsetAsync(dE, 0, std::max<size_t>(n_win * E * 4, 4), c->stream));
+    CUX(cudaMemsetAsync(dM, 0, std::max<size_t>(n_win * E * 4, 4), c->stream));
+    DecodeParams p = {};
+    p.sym = reinterpret_cast<const float2 *>(d_sym);
+    p.n_sym = (long long)(n_win * N);
+    p.n_win = (long long)n_win;
+    p.max_iters = max_iters; p.early_stop = early_stop ? 1 : 0; p.thr = c->t.M / 8;
+    p.out_bytes = d_bytes; p.out_iters = d_iters;
+    p.dbgL = dL; p.dbgE = dE; p.dbgM = dM;
+    st = launch_decode(c, fam, LDPC535_METHOD_SUMPRODUCT, true, p, c->stream);
+    if (st) { cleanup(); return st; }
+    if (out_L) CUX(cudaMemcpyAsync(out_L, dL, n_win * N * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_E) CUX(cudaMemcpyAsync(out_E, dE, n_win * E * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_M) CUX(cudaMemcpyAsync(out_M, dM, n_win * E * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_bytes) CUX(cudaMemcpyAsync(out_bytes, d_bytes, n_win * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (out_iters) CUX(cudaMemcpyAsync(out_iters, d_iters, n_win, cudaMemcpyDeviceToHost, c->stream));
+    CUX(cudaStreamSynchronize(c->stream));
+#undef CUX
+    cleanup();
+    return LDPC535_OK;
+}
+
+}  // extern "C"

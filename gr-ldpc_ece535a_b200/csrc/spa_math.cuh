@@ -1,0 +1,144 @@
+// Sum-product node updates shared by every decoder kernel (sm_100a).
+//
+// Reference arithmetic (lib/ldpc_decoder_cb_impl.cc:503-553, fp64):
+//     E_ji = log((1 + T) / (1 - T)),  T = prod_{k != i} tanh(M_jk / 2)
+//     L_i  = sum_j (E_ji + r_i)           (the intrinsic term is added once PER CHECK)
+//     M_ji = sum_{k != j} (E_ki + r_i)
+//
+// fp32 formulation used here.  With e_k = exp(-|M_jk|):  tanh(|M_jk|/2) = (1-e_k)/(1+e_k).
+// Expand prod_{k != i} (1 + e_k x) = even_i + odd_i x  (x^2 = 1; even/odd elementary
+// symmetric sums of the e_k).  Then  prod(1+e_k) = even+odd,  prod(1-e_k) = even-odd and
+//     (1 + |T|) / (1 - |T|) = even_i / odd_i         =>  |E_ji| = ln(even_i) - ln(odd_i).
+// Every term of even/odd is non-negative, so there is no cancellation anywhere: the
+// naive fp32 `1 - T` loses all accuracy once |E| > ~11, this form keeps ~1e-6 relative
+// accuracy until exp(-|M|) underflows (|M| > 87).  The "all but one" products come from
+// prefix/suffix recurrences (2 FMA per step), not from dividing a total (unstable when
+// the excluded edge is the weakest).  Cost per edge and iteration: 3 MUFU (1 ex2 +
+// 2 lg2) instead of the 4 (tanh/exp, rcp, div, log) of the direct form.
+// sign(T) = XOR of the sign bits of the other inputs.  M = 0 gives e = 1, even = odd,
+// E = 0, like tanh(0) = 0 does in the reference.  A padded slot holds M = +inf: e = 0,
+// the identity of the recurrence.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldpc535 {
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+constexpr float kNegLog2e = -1.4426950408889634f;
+constexpr uint32_t kLn2Bits = 0x3f317218u;   // 0.69314718f
+
+// In: m[s] = bit->check messages of one check (padded slots +inf).  Out: m[s] = E.
+template <int DC>
+__device__ __forceinline__ void check_node_spa(float (&m)[DC])
+{
+    float e[DC];
+    uint32_t sx = 0;
+#pragma unroll
+    for (int s = 0; s < DC; s++) {
+        sx ^= __float_as_uint(m[s]);
+        e[s] = ex2_approx(fabsf(m[s]) * kNegLog2e);
+    }
+    // prefix (pe, po)[s] = expansion over slots < s ; suffix (se, so)[s] over slots > s
+    float pe[DC], po[DC], se[DC], so[DC];
+    pe[0] = 1.f; po[0] = 0.f;
+#pragma unroll
+    for (int s = 1; s < DC; s++) {
+        pe[s] = fmaf(e[s - 1], po[s - 1], pe[s - 1]);
+        po[s] = fmaf(e[s - 1], pe[s - 1], po[s - 1]);
+    }
+    se[DC - 1] = 1.f; so[DC - 1] = 0.f;
+#pragma unroll
+    for (int s = DC - 2; s >= 0; s--) {
+        se[s] = fmaf(e[s + 1], so[s + 1], se[s + 1]);
+        so[s] = fmaf(e[s + 1], se[s + 1], so[s + 1]);
+    }
+    const uint32_t base = (sx & 0x80000000u) | kLn2Bits;   // +-ln2 carrying the sign of all inputs
+#pragma unroll
+    for (int s = 0; s < DC; s++) {
+        const float ev = fmaf(po[s], so[s], pe[s] * se[s]);
+        const float od = fmaf(po[s], se[s], pe[s] * so[s]);
+        const float mag = lg2_approx(ev) - lg2_approx(od);
+        const float c = __uint_as_float((__float_as_uint(m[s]) & 0x80000000u) ^ base);
+        m[s] = mag * c;
+    }
+}
+
+// Min-sum check update (decodeLogDomainSimple, lib/ldpc_decoder_cb_impl.cc:349-376):
+//     Lr_ji = (prod_k sign(Lq_jk)) * sign(Lq_ji) * min_{k != i} |Lq_jk|,  sign(0) = 0.
+// Padded slots hold +inf (sign +1, never the minimum).
+template <int DC>
+__device__ __forceinline__ void check_node_minsum(float (&m)[DC])
+{
+    float min1 = __int_as_float(0x7f800000), min2 = min1;   // two smallest magnitudes
+    int arg1 = -1;
+    int prod = 1;
+#pragma unroll
+    for (int s = 0; s < DC; s++) {
+        const float a = fabsf(m[s]);
+        prod *= (m[s] > 0.f) - (m[s] < 0.f);
+        if (a < min1) { min2 = min1; min1 = a; arg1 = s; }
+        else if (a < min2) { min2 = a; }
+    }
+#pragma unroll
+    for (int s = 0; s < DC; s++) {
+        const int sg = prod * ((m[s] > 0.f) - (m[s] < 0.f));
+        const float mn = (s == arg1) ? min2 : min1;
+        m[s] = (float)sg * mn;
+    }
+}
+
+// Variable update.  q_k = E_k + r for the dv real edges (checks ascending), 0 beyond.
+//   L   = q_0 + q_1 + ...            (lib/ldpc_decoder_cb_impl.cc:519-525)
+//   M_k = sum_{p != k} q_p            (:540-553)
+// as prefix + suffix sums; for dv <= 3 this is the reference's own order of additions.
+template <int DV>
+__device__ __forceinline__ float var_node_spa(float (&x)[DV], int dv, float r)
+{
+    float q[DV], pre[DV], suf[DV];     // pre[k] = q_0+..+q_k ; suf[k] = q_k+..+q_{DV-1}
+#pragma unroll
+    for (int k = 0; k < DV; k++) q[k] = (k < dv) ? x[k] + r : 0.f;
+    pre[0] = q[0];
+#pragma unroll
+    for (int k = 1; k < DV; k++) pre[k] = pre[k - 1] + q[k];
+    suf[DV - 1] = q[DV - 1];
+#pragma unroll
+    for (int k = DV - 2; k >= 0; k--) suf[k] = q[k] + suf[k + 1];
+    if (DV == 1) {
+        x[0] = 0.f;
+    } else {
+        x[0] = suf[1];
+        x[DV - 1] = pre[DV - 2];
+#pragma unroll
+        for (int k = 1; k < DV - 1; k++) x[k] = pre[k - 1] + suf[k + 1];
+    }
+    return pre[DV - 1];
+}
+
+// Min-sum variable update (lib/ldpc_decoder_cb_impl.cc:378-403):
+//   sum = Lr_0 + Lr_1 + ... ;  Lq_k = (Lc + sum) - Lr_k ;  LQ = Lc + sum.
+template <int DV>
+__device__ __forceinline__ float var_node_minsum(float (&x)[DV], int dv, float lc)
+{
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < DV; k++) sum += (k < dv) ? x[k] : 0.f;
+    const float LQ = lc + sum;
+#pragma unroll
+    for (int k = 0; k < DV; k++) x[k] = LQ - x[k];
+    return LQ;
+}
+
+}  // namespace ldpc535
