@@ -1,15 +1,254 @@
-// Placeholder until the specialised thread-per-codeword kernel for the shipped 32x64
-// code lands: reports "not this code" so dispatch stays on the generic kernels.
+// Thread-per-codeword sum-product kernel specialised for the 32x64 code the reference blocks
+// are hard-wired to (lib/ldpc_decoder_cb_impl.cc:39-40, :60-96).
+//
+// The re-ordered H (the constructor's reorderHMatrix, :255-307) is evaluated at COMPILE TIME
+// from the literal in ldpc535_default_code.h, and every edge of the Tanner graph becomes a
+// template constant: the iteration body is straight-line code with exact node degrees (no
+// padded slots, no adjacency-table loads, no shuffles or ballots).  One thread owns one
+// codeword: its 64 intrinsic values live in registers, its 168 edge messages in a private
+// shared-memory column (message e of thread t at ms[e * NT + t]: every warp access is
+// conflict-free and needs no synchronisation).  The arithmetic is spa_math.cuh's, in the
+// same operation order as the generic kernels, so all kernel families agree to the bit.
+// A handle dispatches here only after checking its run-time tables against these
+// compile-time ones (tables_match_c4).
 #pragma once
+#include <utility>
+
 #include "code_tables.h"
 #include "decode_kernels.cuh"
+#include "ldpc535_default_code.h"
+
+namespace ldpc535 {
+namespace c4 {
+
+constexpr int kM = LDPC535_DEFAULT_M, kN = LDPC535_DEFAULT_N, kE = LDPC535_DEFAULT_E;
+static_assert(kM == 32 && kN == 64, "the thread kernel packs hard decisions in two words");
+
+struct Tables {
+    int pivots[kM];
+    int row_ptr[kM + 1];
+    int col_idx[kE];        // re-ordered columns, ascending within a row (CSR edge order)
+    int col_ptr[kN + 1];
+    int edge_of_col[kE];    // CSR edge ids of a column, rows ascending
+    unsigned row_lo[kM], row_hi[kM];
+    bool ok;
+};
+
+// reorderHMatrix ("First" pivot strategy) on 64-bit rows, then CSR/CSC of the permuted H.
+constexpr Tables make_tables()
+{
+    Tables t = {};
+    unsigned long long F[kM] = {}, H[kM] = {};
+    for (int j = 0; j < kM; j++)
+        for (int e = ldpc535_default_row_ptr[j]; e < ldpc535_default_row_ptr[j + 1]; e++)
+            F[j] |= 1ull << ldpc535_default_col_idx[e];
+    for (int j = 0; j < kM; j++) H[j] = F[j];
+    t.ok = true;
+    for (int i = 0; i < kM; i++) {
+        int chosen = -1;
+        for (int c = i; c < kN; c++)
+            if ((F[i] >> c) & 1ull) { chosen = c; break; }
+        if (chosen < 0) { chosen = 0; t.ok = false; }
+        t.pivots[i] = chosen;
+        if (chosen != i) {
+            for (int r = 0; r < kM; r++) {
+                if (((F[r] >> i) ^ (F[r] >> chosen)) & 1ull) F[r] ^= (1ull << i) | (1ull << chosen);
+                if (((H[r] >> i) ^ (H[r] >> chosen)) & 1ull) H[r] ^= (1ull << i) | (1ull << chosen);
+            }
+        }
+        for (int k = i + 1; k < kM; k++)
+            if ((F[k] >> i) & 1ull) F[k] ^= F[i];
+    }
+    int e = 0;
+    for (int j = 0; j < kM; j++) {
+        t.row_ptr[j] = e;
+        for (int c = 0; c < kN; c++)
+            if ((H[j] >> c) & 1ull) t.col_idx[e++] = c;
+        t.row_lo[j] = (unsigned)(H[j] & 0xffffffffull);
+        t.row_hi[j] = (unsigned)(H[j] >> 32);
+    }
+    t.row_ptr[kM] = e;
+    if (e != kE) t.ok = false;
+    int q = 0;
+    for (int c = 0; c < kN; c++) {
+        t.col_ptr[c] = q;
+        for (int j = 0; j < kM; j++)
+            for (int k = t.row_ptr[j]; k < t.row_ptr[j + 1]; k++)
+                if (t.col_idx[k] == c) t.edge_of_col[q++] = k;
+    }
+    t.col_ptr[kN] = q;
+    return t;
+}
+
+constexpr Tables kT = make_tables();
+static_assert(kT.ok, "the shipped code must have an LU pivot order");
+
+template <int... Is, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F &&f)
+{
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<F &&>(f));
+}
+
+// Threads per CTA / CTAs per SM: 672 B of messages per thread, two CTAs share the 227 KB.
+constexpr int kThreads = 160;
+constexpr int kCtasPerSm = 2;
+constexpr size_t kSmemBytes = (size_t)kThreads * kE * sizeof(float);
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+decode_c4_thread_kernel(const DecodeParams p)
+{
+    extern __shared__ float c4_smem[];
+    constexpr int NT = kThreads;
+    float *ms = c4_smem + threadIdx.x;
+    const long long stride = (long long)gridDim.x * NT;
+
+    for (long long w = (long long)blockIdx.x * NT + threadIdx.x; w < p.n_win; w += stride) {
+        const long long off = p.win_offset ? p.win_offset[w] : w * (long long)kN;
+        const float npol = p.polarity ? -(float)p.polarity[w] : -1.f;
+        const bool ok = off >= 0 && off + kN <= p.n_sym;
+
+        // ---- r_i = -pol * Re(sym_i)  (lib/ldpc_decoder_cb_impl.cc:149-153, :486) ----
+        float r[kN];
+        if (ok) {
+            const float2 *s = p.sym + off;
+            if ((off & 1) == 0) {
+                const float4 *s4 = reinterpret_cast<const float4 *>(s);
+#pragma unroll
+                for (int i = 0; i < kN / 2; i++) {
+                    const float4 v = __ldg(s4 + i);
+                    r[2 * i] = npol * v.x;
+                    r[2 * i + 1] = npol * v.z;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kN; i++) r[i] = npol * __ldg(&s[i].x);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kN; i++) r[i] = 0.f;
+        }
+        // M_ji = r_i on every edge (:489-496)
+        static_for<kE>([&](auto ec) {
+            constexpr int e = decltype(ec)::value;
+            constexpr int c = kT.col_idx[e];
+            ms[e * NT] = r[c];
+        });
+
+        unsigned h0 = 0, h1 = 0;
+        int cnt = 0, iters = p.max_iters;
+        bool broke = false;
+        for (int h = 0; h < p.max_iters; h++) {
+            // ---- Step 1: check messages, in place (:503-516) ----
+            static_for<kM>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                constexpr int a = kT.row_ptr[j];
+                constexpr int d = kT.row_ptr[j + 1] - a;
+                float m[d];
+#pragma unroll
+                for (int s = 0; s < d; s++) m[s] = ms[(a + s) * NT];
+                if (DEBUG && p.dbgM) {
+#pragma unroll
+                    for (int s = 0; s < d; s++) p.dbgM[w * kE + a + s] = m[s];
+                }
+                check_node_spa<d>(m);
+#pragma unroll
+                for (int s = 0; s < d; s++) ms[(a + s) * NT] = m[s];
+                if (DEBUG && p.dbgE) {
+#pragma unroll
+                    for (int s = 0; s < d; s++) p.dbgE[w * kE + a + s] = m[s];
+                }
+            });
+            // ---- Test (:519-532) fused with Step 2 (:540-553) ----
+            h0 = 0; h1 = 0;
+            static_for<kN>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int a = kT.col_ptr[i];
+                constexpr int dv = kT.col_ptr[i + 1] - a;
+                float L = 0.f;
+                if constexpr (dv > 0) {
+                    float x[dv];
+                    static_for<dv>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        constexpr int e = kT.edge_of_col[a + k];
+                        x[k] = ms[e * NT];
+                    });
+                    L = var_node_spa<dv>(x, dv, r[i]);
+                    static_for<dv>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        constexpr int e = kT.edge_of_col[a + k];
+                        ms[e * NT] = x[k];
+                    });
+                }
+                if (DEBUG && p.dbgL) p.dbgL[w * kN + i] = L;
+                const unsigned bit = (L <= 0.f) ? 1u : 0u;          // :527
+                if constexpr (i < 32) h0 |= bit << i; else h1 |= bit << (i - 32);
+            });
+            // ---- Finished? (:535-537): every iteration, the last included ----
+            if (p.early_stop || h + 1 == p.max_iters) {
+                cnt = 0;
+                static_for<kM>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr unsigned lo = kT.row_lo[j], hi = kT.row_hi[j];
+                    cnt += __popc((h0 & lo) ^ (h1 & hi)) & 1;
+                });
+                if (p.early_stop && cnt == 0) { iters = h + 1; broke = true; break; }
+            }
+        }
+        if (DEBUG && p.dbgM && !broke) {
+            static_for<kE>([&](auto ec) {
+                constexpr int e = decltype(ec)::value;
+                p.dbgM[w * kE + e] = ms[e * NT];
+            });
+        }
+
+        // ---- outputs: bits 32..63 MSB first (:207-219), checkFrame weight (:236-253) ----
+        if (ok) {
+            const unsigned bytes = __byte_perm(__brev(h1), 0, 0x0123);
+            *reinterpret_cast<unsigned *>(p.out_bytes + w * 4) = bytes;
+            if (p.out_synd) p.out_synd[w] = (uint8_t)min(cnt, p.thr + 1);
+            if (p.out_iters) p.out_iters[w] = (uint8_t)min(iters, 255);
+        } else {
+            *reinterpret_cast<unsigned *>(p.out_bytes + w * 4) = 0u;
+            if (p.out_synd) p.out_synd[w] = 255;
+            if (p.out_iters) p.out_iters[w] = 255;
+        }
+    }
+}
+
+}  // namespace c4
+
+inline cudaError_t launch_c4_thread(const DecodeParams &p, bool dbg, int sm_count, cudaStream_t st)
+{
+    auto kern = dbg ? c4::decode_c4_thread_kernel<true> : c4::decode_c4_thread_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)c4::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    const long long ctas = (p.n_win + c4::kThreads - 1) / c4::kThreads;
+    long long grid = (long long)sm_count * c4::kCtasPerSm;
+    if (ctas < grid) grid = ctas;
+    kern<<<(int)grid, c4::kThreads, c4::kSmemBytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace ldpc535
 
 namespace {
-inline bool tables_match_c4(const ldpc535::CodeTables &) { return false; }
-}
-namespace ldpc535 {
-inline cudaError_t launch_c4_thread(const DecodeParams &, bool, int, cudaStream_t)
+// The handle's run-time tables equal the compile-time ones of the specialised kernel.
+inline bool tables_match_c4(const ldpc535::CodeTables &t)
 {
-    return cudaErrorNotSupported;
+    using namespace ldpc535::c4;
+    if (t.M != kM || t.N != kN || t.E != kE) return false;
+    for (int j = 0; j <= kM; j++) if (t.row_ptr[j] != kT.row_ptr[j]) return false;
+    for (int e = 0; e < kE; e++) if (t.col_idx[e] != kT.col_idx[e]) return false;
+    for (int c = 0; c <= kN; c++) if (t.col_ptr[c] != kT.col_ptr[c]) return false;
+    for (int e = 0; e < kE; e++) if (t.edge_of_col[e] != kT.edge_of_col[e]) return false;
+    for (int j = 0; j < kM; j++) if (t.pivots[j] != kT.pivots[j]) return false;
+    return true;
 }
-}
+}  // namespace

@@ -51,25 +51,35 @@ __device__ __forceinline__ void check_node_spa(float (&m)[DC])
         sx ^= __float_as_uint(m[s]);
         e[s] = ex2_approx(fabsf(m[s]) * kNegLog2e);
     }
-    // prefix (pe, po)[s] = expansion over slots < s ; suffix (se, so)[s] over slots > s
+    // prefix (pe, po)[s] = expansion over slots < s ; suffix (se, so)[s] over slots > s.
+    // The first step of each recurrence and the two end combinations below are written out
+    // (fma(e, 0, 1) = 1, fma(e, 1, 0) = e: exact), so a check evaluated with its exact degree
+    // and the same check padded with e = 0 slots give the same bits.
     float pe[DC], po[DC], se[DC], so[DC];
     pe[0] = 1.f; po[0] = 0.f;
+    if constexpr (DC > 1) { pe[1] = 1.f; po[1] = e[0]; }
 #pragma unroll
-    for (int s = 1; s < DC; s++) {
+    for (int s = 2; s < DC; s++) {
         pe[s] = fmaf(e[s - 1], po[s - 1], pe[s - 1]);
         po[s] = fmaf(e[s - 1], pe[s - 1], po[s - 1]);
     }
     se[DC - 1] = 1.f; so[DC - 1] = 0.f;
+    if constexpr (DC > 1) { se[DC - 2] = 1.f; so[DC - 2] = e[DC - 1]; }
 #pragma unroll
-    for (int s = DC - 2; s >= 0; s--) {
+    for (int s = DC - 3; s >= 0; s--) {
         se[s] = fmaf(e[s + 1], so[s + 1], se[s + 1]);
         so[s] = fmaf(e[s + 1], se[s + 1], so[s + 1]);
     }
     const uint32_t base = (sx & 0x80000000u) | kLn2Bits;   // +-ln2 carrying the sign of all inputs
 #pragma unroll
     for (int s = 0; s < DC; s++) {
-        const float ev = fmaf(po[s], so[s], pe[s] * se[s]);
-        const float od = fmaf(po[s], se[s], pe[s] * so[s]);
+        float ev, od;
+        if (s == 0) { ev = se[0]; od = so[0]; }
+        else if (s == DC - 1) { ev = pe[s]; od = po[s]; }
+        else {
+            ev = fmaf(po[s], so[s], pe[s] * se[s]);
+            od = fmaf(po[s], se[s], pe[s] * so[s]);
+        }
         const float mag = lg2_approx(ev) - lg2_approx(od);
         const float c = __uint_as_float((__float_as_uint(m[s]) & 0x80000000u) ^ base);
         m[s] = mag * c;
@@ -116,7 +126,7 @@ __device__ __forceinline__ float var_node_spa(float (&x)[DV], int dv, float r)
     suf[DV - 1] = q[DV - 1];
 #pragma unroll
     for (int k = DV - 2; k >= 0; k--) suf[k] = q[k] + suf[k + 1];
-    if (DV == 1) {
+    if constexpr (DV == 1) {
         x[0] = 0.f;
     } else {
         x[0] = suf[1];

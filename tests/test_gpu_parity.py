@@ -1,0 +1,438 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI
+(include/ldpc535.h via the ctypes host package), against the CPU oracle on the same seeded
+inputs, against the committed golden fixtures, and -- at sizes the oracle cannot reach --
+through size-independent properties (H c = 0, encode -> decode round trips, linearity).
+
+Bars: encoder / syndromes / hard decisions / iteration counts bit-exact; sum-product
+messages |gpu - ref| <= 1e-4 |ref| + 2e-6 against the fp64 oracle (the kernels compute in
+fp32; the absolute floor covers messages that are ~0)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ldpc_ece535a as L
+from oracle import oracle as O
+import util
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL, ATOL = 1e-4, 2e-6
+
+C4_KERNELS = ["warp", "block", "c4-thread"]
+
+
+@pytest.fixture(scope="module")
+def c4():
+    code = L.Code(None, device=0)
+    yield code
+    code.close()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "c4_golden.npz"))
+
+
+def with_kernel(code, name):
+    try:
+        code.set_kernel(name)
+    except L.Ldpc535Error as e:
+        pytest.skip("kernel family %s not available: %s" % (name, e))
+
+
+def bits_to_cw_sym(cw_bits):
+    return util.bpsk(cw_bits)
+
+
+def sym_to_bits(sym):
+    s = np.asarray(sym).reshape(-1)
+    assert np.all(s.imag == 0) and np.all(np.abs(s.real) == 1)
+    return (s.real > 0).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------
+# encoder
+# ---------------------------------------------------------------------------------------
+def test_encoder_reference_qa_kat(ref_codes):
+    """The reference's own encoder known-answer test (python/qa_ldpc_encoder_bc.py:23-46),
+    on the 8x16 code it was written for, through the CUDA path."""
+    with open(os.path.join(GOLD, "ref_qa_kat.json")) as f:
+        k = json.load(f)
+    frames = []
+    for c, d in zip(k["mod_check"], k["mod_data"]):
+        frames += c + d
+    code = L.Code(ref_codes[k["code"]]["H"], device=0)
+    out = code.encode(np.array(k["data_bytes"], np.uint8))
+    assert np.array_equal(out.reshape(-1), np.array(frames, np.complex64))
+
+
+def test_encoder_golden_source_words(c4, gold):
+    """apps/test_data.h:180-213 source words -> frozen oracle codewords."""
+    out = c4.encode(util.pack_bits_msb(gold["enc_data_bits"]))
+    assert out.shape == (30, 64)
+    assert np.array_equal(sym_to_bits(out).reshape(30, 64), gold["enc_codewords"])
+
+
+@pytest.mark.parametrize("name", ["hData1", "hData2", "hData3", "hData4", "hData5"])
+def test_encoder_vs_oracle_all_reference_codes(ref_codes, name):
+    H = ref_codes[name]["H"]
+    Hp, Lm, Um, _ = O.reorder_h(H)
+    M, N = H.shape
+    K = N - M
+    code = L.Code(H, device=0)
+    rng = np.random.default_rng(11)
+    n = 257                                               # ragged: not a multiple of any tile
+    data = rng.integers(0, 2, (n, K)).astype(np.int32)
+    if K % 8:
+        pytest.skip("K not a whole number of bytes: the reference block cannot frame it")
+    out = code.encode(util.pack_bits_msb(data))
+    want = util.oracle_encode_bits(data, Hp, Lm, Um)
+    assert np.array_equal(sym_to_bits(out).reshape(n, N), want)
+    # every codeword satisfies every check of the re-ordered H
+    assert not ((want @ Hp.T) % 2).any()
+    code.close()
+
+
+def test_encoder_block_level_matches_oracle_work(c4, shipped):
+    """Byte stream -> symbol stream exactly as ldpc_encoder_bc_impl::general_work emits it."""
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, 4 * 1000).astype(np.uint8)
+    want, consumed = O.encoder_work(shipped["Hp"], shipped["L"], shipped["U"], data, 1000 * 64)
+    assert consumed == data.size
+    got = c4.encode(data).reshape(-1)
+    assert np.array_equal(got, want)
+
+
+def test_encoder_empty_and_single(c4):
+    assert c4.encode(np.zeros(0, np.uint8)).shape == (0, 64)
+    one = c4.encode(np.zeros(4, np.uint8))
+    assert np.array_equal(one.reshape(-1), np.full(64, -1 + 0j, np.complex64))
+    with pytest.raises(ValueError):
+        c4.encode(np.zeros(3, np.uint8))
+
+
+def test_encoder_linearity_and_syndrome_1m(c4, shipped):
+    """1 Mi random words: H c = 0 for every frame and enc(a ^ b) = enc(a) ^ enc(b)."""
+    rng = np.random.default_rng(6)
+    n = 1 << 20
+    a = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    b = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    ca = (c4.encode(a).real > 0)
+    cb = (c4.encode(b).real > 0)
+    cab = (c4.encode(a ^ b).real > 0)
+    assert np.array_equal(ca ^ cb, cab)
+    Hp = shipped["Hp"].astype(np.uint8)
+    synd = (ca.astype(np.uint8) @ Hp.T) & 1
+    assert not synd.any()
+    # data bits are carried verbatim in the second half
+    assert np.array_equal(np.packbits(ca[:, 32:], axis=1), a)
+
+
+# ---------------------------------------------------------------------------------------
+# decoder: goldens and oracle parity on the shipped code
+# ---------------------------------------------------------------------------------------
+POINTS = (("2dB_5it", 5, 1), ("4dB_5it", 5, 1), ("2dB_50it_noearly", 50, 0), ("clean_5it", 5, 1))
+
+
+@pytest.mark.parametrize("kernel", C4_KERNELS)
+@pytest.mark.parametrize("tag,iters,early", POINTS)
+def test_decoder_spa_goldens(c4, gold, kernel, tag, iters, early):
+    with_kernel(c4, kernel)
+    b, sy, it = c4.decode(gold["dec_%s_sym" % tag], method=1, max_iters=iters, early_stop=early)
+    assert np.array_equal(b, gold["dec_%s_spa_bytes" % tag])
+    assert np.array_equal(it, gold["dec_%s_spa_iters" % tag])
+    assert np.array_equal(sy, gold["dec_%s_spa_synd" % tag])
+    c4.set_kernel(None)
+
+
+@pytest.mark.parametrize("kernel", ["warp", "block"])
+@pytest.mark.parametrize("tag,iters,early", POINTS)
+def test_decoder_minsum_goldens(c4, gold, kernel, tag, iters, early):
+    with_kernel(c4, kernel)
+    b, sy, it = c4.decode(gold["dec_%s_sym" % tag], method=0, max_iters=iters, early_stop=early)
+    assert np.array_equal(b, gold["dec_%s_minsum_bytes" % tag])
+    assert np.array_equal(it, gold["dec_%s_minsum_iters" % tag])
+    assert np.array_equal(sy, gold["dec_%s_minsum_synd" % tag])
+    c4.set_kernel(None)
+
+
+@pytest.mark.parametrize("kernel", C4_KERNELS)
+@pytest.mark.parametrize("ebn0,iters,early", [(0.0, 5, 1), (2.0, 5, 1), (4.0, 5, 1), (6.0, 5, 1),
+                                              (2.0, 50, 0), (2.0, 50, 1), (4.0, 1, 1)])
+def test_decoder_spa_vs_oracle_fixed_seed(c4, shipped, kernel, ebn0, iters, early):
+    """Config 1: 1 000 seeded codewords, encode -> BPSK + AWGN -> sum-product; hard
+    decisions, iteration counts and saturating syndrome weights identical to the oracle."""
+    with_kernel(c4, kernel)
+    n = 1000 if iters <= 5 else 300
+    _, _, sym = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], n, ebn0,
+                                  seed=int(ebn0 * 10) + iters)
+    wb, wit, wsy = util.oracle_spa_batch(sym, shipped["Hp"], iters, early)
+    b, sy, it = c4.decode(sym, method=1, max_iters=iters, early_stop=early)
+    assert np.array_equal(b, wb)
+    assert np.array_equal(it, wit)
+    assert np.array_equal(sy, wsy)
+    c4.set_kernel(None)
+
+
+@pytest.mark.parametrize("method", [0, 2, 3, 7])
+@pytest.mark.parametrize("kernel", ["warp", "block"])
+def test_decoder_other_methods_vs_oracle(c4, shipped, method, kernel):
+    """min-sum (0 and any unknown value), bit-flip (2), hard (3)."""
+    with_kernel(c4, kernel)
+    _, _, sym = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], 500, 3.0, seed=77)
+    wb, wit, wsy, _ = O.decode_frames(sym, shipped["Hp"], method=method, iterations=5,
+                                      early_stop=True, threads=4)
+    b, sy, it = c4.decode(sym, method=method, max_iters=5)
+    assert np.array_equal(b, wb)
+    assert np.array_equal(sy, wsy)
+    if method in (0, 7):
+        assert np.array_equal(it, wit)
+    c4.set_kernel(None)
+
+
+@pytest.mark.parametrize("kernel", C4_KERNELS)
+def test_decoder_messages_within_tolerance(c4, shipped, kernel):
+    """L, E, M after 1..5 iterations against the fp64 oracle: rtol 1e-4 (+ 2e-6 floor)."""
+    with_kernel(c4, kernel)
+    Hp = shipped["Hp"]
+    rows, cols = np.nonzero(Hp)
+    _, _, sym = util.synth_frames(Hp, shipped["L"], shipped["U"], 48, 2.0, seed=123)
+    for iters, early in ((1, 0), (2, 0), (5, 0), (5, 1)):
+        got = c4.decode_debug(sym, max_iters=iters, early_stop=early, kernel=kernel)
+        for f in range(sym.shape[0]):
+            vhat, run, Lr, Er, Mr = O.decode_spa(sym[f].real, Hp, iters, early, debug=True)
+            assert got["iters"][f] == run
+            for name, ref in (("L", Lr), ("E", Er[rows, cols]), ("M", Mr[rows, cols])):
+                g = got[name][f].astype(np.float64)
+                assert np.all(np.abs(g - ref) <= RTOL * np.abs(ref) + ATOL), (
+                    kernel, iters, early, f, name, np.max(np.abs(g - ref)))
+    c4.set_kernel(None)
+
+
+@pytest.mark.parametrize("kernel", C4_KERNELS)
+def test_decoder_reference_qa_kat_shape_noiseless(c4, shipped, kernel):
+    """Noiseless frames decode to their data in one iteration with zero syndrome."""
+    with_kernel(c4, kernel)
+    data, cw, sym = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], 333, None, seed=1)
+    b, sy, it = c4.decode(sym, method=1)
+    assert np.array_equal(b, util.pack_bits_msb(data))
+    assert (sy == 0).all() and (it == 1).all()
+    c4.set_kernel(None)
+
+
+def test_decoder_reference_qa_kat(ref_codes):
+    """python/qa_ldpc_decoder_cb.py:20-43 on the 8x16 code, every method."""
+    with open(os.path.join(GOLD, "ref_qa_kat.json")) as f:
+        k = json.load(f)
+    frames = []
+    for c, d in zip(k["mod_check"], k["mod_data"]):
+        frames += c + d
+    code = L.Code(ref_codes[k["code"]]["H"], device=0)
+    for method in (0, 1, 2, 3):
+        b, sy, it = code.decode(np.array(frames, np.complex64), method=method)
+        assert list(b.reshape(-1)) == k["data_bytes"]
+        assert (sy == 0).all()
+    code.close()
+
+
+@pytest.mark.parametrize("kernel", C4_KERNELS)
+def test_decoder_windows_and_polarity(c4, shipped, kernel):
+    """Arbitrary symbol offsets and -1 polarity (the sync machine's slide / inverted retry,
+    lib/ldpc_decoder_cb_impl.cc:151-152, :178-199) equal the oracle on the shifted, negated
+    window."""
+    with_kernel(c4, kernel)
+    Hp = shipped["Hp"]
+    _, _, sym = util.synth_frames(Hp, shipped["L"], shipped["U"], 40, 3.0, seed=8)
+    stream = sym.reshape(-1)
+    rng = np.random.default_rng(9)
+    offs = rng.integers(0, stream.size - 64 + 1, 300).astype(np.int64)
+    offs[:3] = (0, stream.size - 64, 1)
+    pol = rng.choice(np.array([-1, 1], np.int8), 300)
+    wins = np.stack([stream[o:o + 64] * p for o, p in zip(offs, pol)])
+    wb, wit, wsy = util.oracle_spa_batch(wins, Hp, 5, True)
+    b, sy, it = c4.decode(stream, method=1, win_offset=offs, polarity=pol)
+    assert np.array_equal(b, wb) and np.array_equal(it, wit) and np.array_equal(sy, wsy)
+    with pytest.raises(L.Ldpc535Error):
+        c4.decode(stream, win_offset=np.array([stream.size - 63], np.int64))
+    with pytest.raises(L.Ldpc535Error):
+        c4.decode(stream, win_offset=np.array([-1], np.int64))
+    c4.set_kernel(None)
+
+
+@pytest.mark.parametrize("kernel", C4_KERNELS)
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 1025])
+def test_decoder_ragged_batches(c4, shipped, kernel, n):
+    with_kernel(c4, kernel)
+    _, _, sym = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], max(n, 1), 2.0, seed=n)
+    sym = sym[:n]
+    b, sy, it = c4.decode(sym.reshape(-1), method=1, n_win=n)
+    if n:
+        wb, wit, wsy = util.oracle_spa_batch(sym, shipped["Hp"], 5, True)
+        assert np.array_equal(b, wb) and np.array_equal(it, wit) and np.array_equal(sy, wsy)
+    else:
+        assert b.shape == (0, 4)
+    c4.set_kernel(None)
+
+
+def test_decoder_kernel_families_agree_1m(c4, shipped):
+    """1 Mi noisy frames: every kernel family returns the same bytes / iterations /
+    syndromes (a checksum of checksums across implementations), and the noiseless
+    round trip returns the data."""
+    rng = np.random.default_rng(10)
+    n = 1 << 20
+    data = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    clean = c4.encode(data)
+    b, sy, it = c4.decode(clean, method=1)
+    assert np.array_equal(b, data) and not sy.any() and (it == 1).all()
+    sigma = np.float32(np.sqrt(10.0 ** (-2.0 / 10.0)))
+    noisy = clean.copy()
+    noisy.real += rng.standard_normal(clean.shape, dtype=np.float32) * sigma
+    res = {}
+    for kern in C4_KERNELS:
+        try:
+            c4.set_kernel(kern)
+        except L.Ldpc535Error:
+            continue
+        res[kern] = c4.decode(noisy, method=1)
+    c4.set_kernel(None)
+    assert len(res) >= 2
+    base = res.pop("warp")
+    for kern, r in res.items():
+        for a, b2 in zip(base, r):
+            assert np.array_equal(a, b2), kern
+    # spot-check 2 000 of them against the oracle
+    idx = rng.choice(n, 2000, replace=False)
+    wb, wit, wsy = util.oracle_spa_batch(noisy[idx], shipped["Hp"], 5, True)
+    assert np.array_equal(base[0][idx], wb)
+    assert np.array_equal(base[2][idx], wit)
+    assert np.array_equal(base[1][idx], wsy)
+
+
+# ---------------------------------------------------------------------------------------
+# other reference codes and the n = 8192 code (CTA-per-codeword kernel)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["hData1", "hData2", "hData5"])
+def test_decoder_other_reference_codes(ref_codes, name):
+    H = ref_codes[name]["H"]
+    Hp, Lm, Um, _ = O.reorder_h(H)
+    if (H.shape[1] - H.shape[0]) % 8:
+        pytest.skip("K not a whole number of bytes")
+    code = L.Code(H, device=0)
+    _, _, sym = util.synth_frames(Hp, Lm, Um, 200, 4.0, seed=3)
+    for method in (1, 0):
+        wb, wit, wsy, _ = O.decode_frames(sym, Hp, method=method, iterations=5, early_stop=True,
+                                          threads=4)
+        b, sy, it = code.decode(sym, method=method)
+        assert np.array_equal(b, wb) and np.array_equal(it, wit) and np.array_equal(sy, wsy)
+    code.close()
+
+
+@pytest.fixture(scope="module")
+def c8k():
+    code, seed = L.codes.first_invertible(n=8192, seed=535, device=0)
+    yield code
+    code.close()
+
+
+def c8k_tables(code):
+    row_ptr, col_idx = code.h_csr()
+    rows = np.repeat(np.arange(code.M), np.diff(row_ptr))
+    order = np.lexsort((rows, col_idx))
+    col_ptr = np.zeros(code.N + 1, np.int32)
+    np.add.at(col_ptr, col_idx + 1, 1)
+    return (row_ptr, col_idx, np.cumsum(col_ptr).astype(np.int32), order.astype(np.int32)), rows
+
+
+def test_c8k_encode_satisfies_every_check(c8k):
+    rng = np.random.default_rng(12)
+    n = 300
+    data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
+    out = c8k.encode(data)
+    bits = sym_to_bits(out).reshape(n, c8k.N)
+    (row_ptr, col_idx, _, _), rows = c8k_tables(c8k)
+    for f in range(n):
+        synd = np.bincount(rows, weights=bits[f][col_idx], minlength=c8k.M).astype(np.int64) & 1
+        assert not synd.any()
+    assert np.array_equal(np.packbits(bits[:, c8k.M:], axis=1), data)
+    # generator parity equals the host table product
+    P = c8k.generator()
+    d = np.unpackbits(data[0]).astype(np.uint64)
+    dw = (d.reshape(-1, 32) << np.arange(32, dtype=np.uint64)).sum(1).astype(np.uint32)
+    anded = P & dw
+    c = np.zeros(c8k.M, np.int64)
+    for sh in range(32):
+        c ^= ((anded >> np.uint32(sh)) & np.uint32(1)).sum(1).astype(np.int64) & 1
+    assert np.array_equal(c, bits[0][:c8k.M])
+
+
+def test_c8k_decode_vs_sparse_oracle(c8k):
+    """Config 4's code: decisions and iteration counts vs the sparse restatement (checked
+    bit-identical to the dense one on the shipped code by the CPU suite)."""
+    rng = np.random.default_rng(13)
+    n = 12
+    data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
+    clean = c8k.encode(data)
+    tables, _ = c8k_tables(c8k)
+    for ebn0, iters in ((4.0, 20), (2.0, 50)):
+        sigma = np.float32(np.sqrt(10.0 ** (-ebn0 / 10.0)))
+        noisy = clean.copy()
+        noisy.real += rng.standard_normal(clean.shape, dtype=np.float32) * sigma
+        b, sy, it = c8k.decode(noisy, method=1, max_iters=iters, early_stop=True)
+        for f in range(n):
+            vhat, run = O.decode_spa_sparse(noisy[f].real, tables, c8k.M, c8k.N, iters, True)
+            assert it[f] == run, (ebn0, f)
+            assert np.array_equal(np.packbits(vhat[c8k.M:].astype(np.uint8)), b[f]), (ebn0, f)
+    b, sy, it = c8k.decode(clean, method=1)
+    assert np.array_equal(b, data) and not sy.any() and (it == 1).all()
+
+
+def test_c8k_messages_within_tolerance(c8k):
+    rng = np.random.default_rng(14)
+    data = rng.integers(0, 256, (2, c8k.nbytes)).astype(np.uint8)
+    noisy = c8k.encode(data)
+    noisy.real += rng.standard_normal(noisy.shape, dtype=np.float32) * np.float32(0.7)
+    tables, _ = c8k_tables(c8k)
+    got = c8k.decode_debug(noisy, max_iters=3, early_stop=False)
+    for f in range(2):
+        vhat, run, Lr, Er, Mr = O.decode_spa_sparse(noisy[f].real, tables, c8k.M, c8k.N, 3, False,
+                                                    debug=True)
+        for name, ref in (("L", Lr), ("E", Er), ("M", Mr)):
+            g = got[name][f].astype(np.float64)
+            assert np.all(np.abs(g - ref) <= RTOL * np.abs(ref) + ATOL), (f, name)
+
+
+# ---------------------------------------------------------------------------------------
+# device-resident API and bookkeeping
+# ---------------------------------------------------------------------------------------
+def test_device_api_matches_host_api(c4, shipped):
+    import torch
+    rng = np.random.default_rng(15)
+    n = 5000
+    data = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    d_in = torch.from_numpy(data).cuda()
+    d_sym = torch.empty((n, 64, 2), dtype=torch.float32, device="cuda")
+    before = c4.launch_count()
+    c4.encode_dev(d_in.data_ptr(), n, d_sym.data_ptr())
+    c4.sync()
+    assert c4.launch_count() == before + 1
+    host = c4.encode(data)
+    assert np.array_equal(d_sym.cpu().numpy().view(np.complex64).reshape(n, 64), host)
+    d_sym[:, :, 0] += 0.8 * torch.randn((n, 64), device="cuda")
+    d_b = torch.empty((n, 4), dtype=torch.uint8, device="cuda")
+    d_s = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_i = torch.empty(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    c4.decode_dev(d_sym.data_ptr(), n * 64, n, d_b.data_ptr(), d_s.data_ptr(), d_i.data_ptr())
+    c4.sync()
+    hb, hs, hi = c4.decode(d_sym.cpu().numpy().view(np.complex64).reshape(n, 64))
+    assert np.array_equal(d_b.cpu().numpy(), hb)
+    assert np.array_equal(d_s.cpu().numpy(), hs)
+    assert np.array_equal(d_i.cpu().numpy(), hi)
+
+
+def test_device_info_is_b200():
+    assert L.device_count() >= 1
+    info = L.device_info(0)
+    assert info["sm"][0] == 10, info
