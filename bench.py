@@ -208,6 +208,8 @@ def run_gpu(args):
 
     n_cw = args.codewords
     code = L.Code(None, device=local)
+    if args.kernel:
+        code.set_kernel(args.kernel)
     stream = torch.cuda.Stream()            # a real stream: NULL would mean "the handle's own"
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
@@ -355,6 +357,7 @@ def main():
     ap.add_argument("--codewords", type=int, default=10_000_000, help="codewords per GPU per step")
     ap.add_argument("--cpu-per-core", type=int, default=4000, help="cpu_baseline sample per host core")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernel", default=None, help="force a decoder kernel family (warp/block/c4-thread)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -94,10 +94,16 @@ __device__ __forceinline__ void static_for(F &&f)
     static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<F &&>(f));
 }
 
-// Threads per CTA / CTAs per SM: 672 B of messages per thread, two CTAs share the 227 KB.
-constexpr int kThreads = 160;
-constexpr int kCtasPerSm = 2;
-constexpr size_t kSmemBytes = (size_t)kThreads * kE * sizeof(float);
+// Occupancy: 12 warps per SM (3 per scheduler, so the four schedulers carry equal work) as
+// three 128-thread CTAs.  The first kSmemEdges messages of a thread live in its shared-memory
+// column (576 B per thread, 216 KB per SM), the remaining kRegEdges in registers; accesses are
+// volatile so the compiler issues real LDS/STS instead of forwarding all 168 values through
+// registers and spilling them to local memory.
+constexpr int kThreads = 128;
+constexpr int kCtasPerSm = 3;
+constexpr int kRegEdges = 24;
+constexpr int kSmemEdges = kE - kRegEdges;
+constexpr size_t kSmemBytes = (size_t)kThreads * kSmemEdges * sizeof(float);
 
 template <bool DEBUG>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -105,7 +111,16 @@ decode_c4_thread_kernel(const DecodeParams p)
 {
     extern __shared__ float c4_smem[];
     constexpr int NT = kThreads;
-    float *ms = c4_smem + threadIdx.x;
+    volatile float *ms = c4_smem + threadIdx.x;
+    float mreg[kRegEdges];
+    auto msg_ld = [&](auto ec) -> float {
+        constexpr int e = decltype(ec)::value;
+        if constexpr (e < kSmemEdges) return ms[e * NT]; else return mreg[e - kSmemEdges];
+    };
+    auto msg_st = [&](auto ec, float v) {
+        constexpr int e = decltype(ec)::value;
+        if constexpr (e < kSmemEdges) ms[e * NT] = v; else mreg[e - kSmemEdges] = v;
+    };
     const long long stride = (long long)gridDim.x * NT;
 
     for (long long w = (long long)blockIdx.x * NT + threadIdx.x; w < p.n_win; w += stride) {
@@ -137,7 +152,7 @@ decode_c4_thread_kernel(const DecodeParams p)
         static_for<kE>([&](auto ec) {
             constexpr int e = decltype(ec)::value;
             constexpr int c = kT.col_idx[e];
-            ms[e * NT] = r[c];
+            msg_st(ec, r[c]);
         });
 
         unsigned h0 = 0, h1 = 0;
@@ -150,15 +165,19 @@ decode_c4_thread_kernel(const DecodeParams p)
                 constexpr int a = kT.row_ptr[j];
                 constexpr int d = kT.row_ptr[j + 1] - a;
                 float m[d];
-#pragma unroll
-                for (int s = 0; s < d; s++) m[s] = ms[(a + s) * NT];
+                static_for<d>([&](auto sc) {
+                    constexpr int s = decltype(sc)::value;
+                    m[s] = msg_ld(std::integral_constant<int, a + s>{});
+                });
                 if (DEBUG && p.dbgM) {
 #pragma unroll
                     for (int s = 0; s < d; s++) p.dbgM[w * kE + a + s] = m[s];
                 }
                 check_node_spa<d>(m);
-#pragma unroll
-                for (int s = 0; s < d; s++) ms[(a + s) * NT] = m[s];
+                static_for<d>([&](auto sc) {
+                    constexpr int s = decltype(sc)::value;
+                    msg_st(std::integral_constant<int, a + s>{}, m[s]);
+                });
                 if (DEBUG && p.dbgE) {
 #pragma unroll
                     for (int s = 0; s < d; s++) p.dbgE[w * kE + a + s] = m[s];
@@ -176,13 +195,13 @@ decode_c4_thread_kernel(const DecodeParams p)
                     static_for<dv>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
                         constexpr int e = kT.edge_of_col[a + k];
-                        x[k] = ms[e * NT];
+                        x[k] = msg_ld(std::integral_constant<int, e>{});
                     });
                     L = var_node_spa<dv>(x, dv, r[i]);
                     static_for<dv>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
                         constexpr int e = kT.edge_of_col[a + k];
-                        ms[e * NT] = x[k];
+                        msg_st(std::integral_constant<int, e>{}, x[k]);
                     });
                 }
                 if (DEBUG && p.dbgL) p.dbgL[w * kN + i] = L;
@@ -203,7 +222,7 @@ decode_c4_thread_kernel(const DecodeParams p)
         if (DEBUG && p.dbgM && !broke) {
             static_for<kE>([&](auto ec) {
                 constexpr int e = decltype(ec)::value;
-                p.dbgM[w * kE + e] = ms[e * NT];
+                p.dbgM[w * kE + e] = msg_ld(ec);
             });
         }
 

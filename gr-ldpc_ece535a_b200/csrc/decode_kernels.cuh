@@ -9,6 +9,8 @@
 // early termination, the saturating syndrome weight and MSB-first byte packing
 // (lib/ldpc_decoder_cb_impl.cc:149-153, :478-557, :236-253, :207-219).
 #pragma once
+#include <type_traits>
+
 #include "spa_math.cuh"
 
 namespace ldpc535 {
@@ -40,13 +42,17 @@ constexpr int kWarpKernelThreads = 128;
 // decode_block_kernel shared-memory layout (host and device must agree):
 //   [0,16) mbarrier | msg[DC*M] f32 | r[N] f32 | hard[ceil(N/32)] | par[ceil(M/32)] | red[4]
 //   | (16-aligned) chk_var copy | var_slot copy
-__host__ __device__ inline size_t block_smem_fixed_bytes(int dc, int M, int N)
+__host__ __device__ inline size_t block_smem_fixed_bytes(int dc, int M, int N, int msg_size = 4)
 {
-    size_t b = 16 + 4 * (size_t)dc * M + 4 * (size_t)N + 4 * (size_t)((N + 31) >> 5) +
+    size_t b = 16 + (size_t)msg_size * dc * M + 4 * (size_t)N + 4 * (size_t)((N + 31) >> 5) +
                4 * (size_t)((M + 31) >> 5) + 16;
     return (b + 15) & ~(size_t)15;
 }
 constexpr float kInf = __builtin_huge_valf();
+
+// message type of a method: fp64 for min-sum (exact, see spa_math.cuh), fp32 otherwise
+template <int METHOD>
+using msg_t = std::conditional_t<METHOD == kMethodMinSum, double, float>;
 
 __device__ __forceinline__ uint8_t pack_msb_first(uint32_t bits8)
 {
@@ -60,10 +66,11 @@ template <int METHOD, int DC, int DV, bool DEBUG>
 __global__ void __launch_bounds__(kWarpKernelThreads)
 decode_warp_kernel(const DecodeParams p)
 {
-    extern __shared__ float smem_f[];
+    using T = msg_t<METHOD>;
+    extern __shared__ __align__(16) unsigned char smem_w[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *msg = smem_f + warp * (DC * 32);          // slot-major strip: msg[s * 32 + check]
+    T *msg = reinterpret_cast<T *>(smem_w) + warp * (DC * 32);   // slot-major strip: msg[s * 32 + check]
     const int M = p.M, N = p.N;
 
     // ---- this lane's rows/columns of H (loop invariant, registers) ----
@@ -95,18 +102,18 @@ decode_warp_kernel(const DecodeParams p)
     }
 #pragma unroll
     for (int s = 0; s < DC; s++)
-        if (s >= cdeg) msg[s * 32 + lane] = kInf;    // padded slots: identity, never rewritten
+        if (s >= cdeg) msg[s * 32 + lane] = (T)kInf; // padded slots: identity, never rewritten
 
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w < p.n_win; w += warps_total) {
         const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
         const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
         const bool ok = off >= 0 && off + N <= p.n_sym;
-        float r[2];
+        T r[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
             const int v = lane + 32 * t;
-            r[t] = (ok && v < N) ? -pol * __ldg(&p.sym[off + v].x) : 0.f;
+            r[t] = (T)((ok && v < N) ? -pol * __ldg(&p.sym[off + v].x) : 0.f);
         }
         uint32_t hard0 = 0, hard1 = 0, bad = 0;
         int iters = 0;
@@ -114,8 +121,8 @@ decode_warp_kernel(const DecodeParams p)
 
         if (METHOD == kMethodHard || METHOD == kMethodBitFlip) {
             // decodeHard / decodeBitFlipping's prior: rx < 0 -> 0 else 1, rx = -r
-            const bool y0 = (lane < N) && !(r[0] > 0.f);
-            const bool y1 = (lane + 32 < N) && !(r[1] > 0.f);
+            const bool y0 = (lane < N) && !(r[0] > (T)0);
+            const bool y1 = (lane + 32 < N) && !(r[1] > (T)0);
             hard0 = __ballot_sync(0xffffffffu, y0);
             hard1 = __ballot_sync(0xffffffffu, y1);
             bad = __ballot_sync(0xffffffffu, (__popc(row_lo & hard0) + __popc(row_hi & hard1)) & 1);
@@ -149,41 +156,41 @@ decode_warp_kernel(const DecodeParams p)
             iters = p.max_iters;
             for (int h = 0; h < p.max_iters; h++) {
                 __syncwarp();
-                float m[DC];
+                T m[DC];
 #pragma unroll
                 for (int s = 0; s < DC; s++) m[s] = msg[s * 32 + lane];
                 if (DEBUG && p.dbgM && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < cdeg) p.dbgM[w * p.E + p.slot_edge[s * M + lane]] = m[s];
+                        if (s < cdeg) p.dbgM[w * p.E + p.slot_edge[s * M + lane]] = (float)m[s];
                 }
-                if (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC>(m);
+                if constexpr (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC, T>(m);
 #pragma unroll
                 for (int s = 0; s < DC; s++)
                     if (s < cdeg) msg[s * 32 + lane] = m[s];
                 if (DEBUG && p.dbgE && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < cdeg) p.dbgE[w * p.E + p.slot_edge[s * M + lane]] = m[s];
+                        if (s < cdeg) p.dbgE[w * p.E + p.slot_edge[s * M + lane]] = (float)m[s];
                 }
                 __syncwarp();
-                float x[2][DV], L[2];
+                T x[2][DV], L[2];
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
 #pragma unroll
                     for (int k = 0; k < DV; k++) x[t][k] = msg[vpos[t][k]];
-                    L[t] = (METHOD == kMethodSpa) ? var_node_spa<DV>(x[t], vdeg[t], r[t])
-                                                  : var_node_minsum<DV>(x[t], vdeg[t], r[t]);
+                    if constexpr (METHOD == kMethodSpa) L[t] = var_node_spa<DV>(x[t], vdeg[t], r[t]);
+                    else L[t] = var_node_minsum<DV, T>(x[t], vdeg[t], r[t]);
                 }
                 // SPA decides 1 on L <= 0 (:527), min-sum on LQ < 0 (:398)
-                const bool b0 = (lane < N) && (METHOD == kMethodSpa ? (L[0] <= 0.f) : (L[0] < 0.f));
-                const bool b1 = (lane + 32 < N) && (METHOD == kMethodSpa ? (L[1] <= 0.f) : (L[1] < 0.f));
+                const bool b0 = (lane < N) && (METHOD == kMethodSpa ? (L[0] <= (T)0) : (L[0] < (T)0));
+                const bool b1 = (lane + 32 < N) && (METHOD == kMethodSpa ? (L[1] <= (T)0) : (L[1] < (T)0));
                 hard0 = __ballot_sync(0xffffffffu, b0);
                 hard1 = __ballot_sync(0xffffffffu, b1);
                 bad = __ballot_sync(0xffffffffu, (__popc(row_lo & hard0) + __popc(row_hi & hard1)) & 1);
                 if (DEBUG && p.dbgL) {
-                    if (lane < N) p.dbgL[w * N + lane] = L[0];
-                    if (lane + 32 < N) p.dbgL[w * N + lane + 32] = L[1];
+                    if (lane < N) p.dbgL[w * N + lane] = (float)L[0];
+                    if (lane + 32 < N) p.dbgL[w * N + lane + 32] = (float)L[1];
                 }
                 // SPA tests every iteration, the last included (:535); min-sum skips the
                 // test on the last one (:406)
@@ -202,7 +209,7 @@ decode_warp_kernel(const DecodeParams p)
                 if (lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < cdeg) p.dbgM[w * p.E + p.slot_edge[s * M + lane]] = msg[s * 32 + lane];
+                        if (s < cdeg) p.dbgM[w * p.E + p.slot_edge[s * M + lane]] = (float)msg[s * 32 + lane];
                 }
             }
         }
@@ -247,13 +254,14 @@ decode_block_kernel(const DecodeParams p)
     const int nwords = (N + 31) >> 5;
 
     // shared layout: bar | msg[DC*M] | r[N] | hard[nwords] | par[(M+31)/32] | red | tabA | tabB
+    using T = msg_t<METHOD>;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    float *msg = reinterpret_cast<float *>(smem_raw + 16);
-    float *r = msg + (size_t)DC * M;
+    T *msg = reinterpret_cast<T *>(smem_raw + 16);
+    float *r = reinterpret_cast<float *>(msg + (size_t)DC * M);
     uint32_t *hard = reinterpret_cast<uint32_t *>(r + N);
     uint32_t *par = hard + nwords;
     int *red = reinterpret_cast<int *>(par + ((M + 31) >> 5));
-    const size_t tab_off = block_smem_fixed_bytes(DC, M, N);
+    const size_t tab_off = block_smem_fixed_bytes(DC, M, N, (int)sizeof(T));
     const uint16_t *chk_var = p.chk_var;
     const uint16_t *var_slot = p.var_slot;
 
@@ -362,30 +370,30 @@ decode_block_kernel(const DecodeParams p)
         } else {
             for (int idx = tid; idx < DC * M; idx += nt) {
                 const int v = chk_var[idx];
-                msg[idx] = (v != 0xFFFF) ? r[v] : kInf;
+                msg[idx] = (T)((v != 0xFFFF) ? r[v] : kInf);
             }
             __syncthreads();
             iters = p.max_iters;
             for (int h = 0; h < p.max_iters; h++) {
                 // ---- check nodes ----
                 for (int j = tid; j < M; j += nt) {
-                    float m[DC];
+                    T m[DC];
 #pragma unroll
                     for (int s = 0; s < DC; s++) m[s] = msg[s * M + j];
                     const int deg = p.chk_deg[j];
                     if (DEBUG && p.dbgM) {
 #pragma unroll
                         for (int s = 0; s < DC; s++)
-                            if (s < deg) p.dbgM[w * p.E + p.slot_edge[s * M + j]] = m[s];
+                            if (s < deg) p.dbgM[w * p.E + p.slot_edge[s * M + j]] = (float)m[s];
                     }
-                    if (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC>(m);
+                    if constexpr (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC, T>(m);
 #pragma unroll
                     for (int s = 0; s < DC; s++)
                         if (s < deg) msg[s * M + j] = m[s];
                     if (DEBUG && p.dbgE) {
 #pragma unroll
                         for (int s = 0; s < DC; s++)
-                            if (s < deg) p.dbgE[w * p.E + p.slot_edge[s * M + j]] = m[s];
+                            if (s < deg) p.dbgE[w * p.E + p.slot_edge[s * M + j]] = (float)m[s];
                     }
                 }
                 __syncthreads();
@@ -394,18 +402,19 @@ decode_block_kernel(const DecodeParams p)
                     const int i = base + tid;
                     bool b = false;
                     if (i < N) {
-                        float x[DV];
+                        T x[DV];
                         int idx[DV], dv = 0;
 #pragma unroll
                         for (int k = 0; k < DV; k++) {
                             idx[k] = var_slot[k * N + i];
-                            x[k] = 0.f;
+                            x[k] = (T)0;
                             if (idx[k] != 0xFFFF) { x[k] = msg[idx[k]]; dv = k + 1; }
                         }
-                        const float L = (METHOD == kMethodSpa) ? var_node_spa<DV>(x, dv, r[i])
-                                                               : var_node_minsum<DV>(x, dv, r[i]);
-                        b = (METHOD == kMethodSpa) ? (L <= 0.f) : (L < 0.f);
-                        if (DEBUG && p.dbgL) p.dbgL[w * N + i] = L;
+                        T L;
+                        if constexpr (METHOD == kMethodSpa) L = var_node_spa<DV>(x, dv, r[i]);
+                        else L = var_node_minsum<DV, T>(x, dv, (T)r[i]);
+                        b = (METHOD == kMethodSpa) ? (L <= (T)0) : (L < (T)0);
+                        if (DEBUG && p.dbgL) p.dbgL[w * N + i] = (float)L;
 #pragma unroll
                         for (int k = 0; k < DV; k++)
                             if (k < dv) msg[idx[k]] = x[k];
@@ -440,7 +449,7 @@ decode_block_kernel(const DecodeParams p)
                     const int deg = p.chk_deg[j];
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < deg) p.dbgM[w * p.E + p.slot_edge[s * M + j]] = msg[s * M + j];
+                        if (s < deg) p.dbgM[w * p.E + p.slot_edge[s * M + j]] = (float)msg[s * M + j];
                 }
             }
         }

@@ -217,7 +217,7 @@ template <int METHOD, int DC, int DV, bool DBG>
 cudaError_t launch_warp(const ldpc535_code *c, const DecodeParams &p, cudaStream_t st)
 {
     const int wpb = kWarpKernelThreads / 32;
-    const size_t smem = sizeof(float) * wpb * DC * 32;
+    const size_t smem = sizeof(msg_t<METHOD>) * wpb * DC * 32;
     long long blocks = (p.n_win + wpb - 1) / wpb;
     const int grid = (int)std::min<long long>(blocks, (long long)c->sm_count * 16);
     decode_warp_kernel<METHOD, DC, DV, DBG><<<grid, kWarpKernelThreads, smem, st>>>(p);
@@ -225,17 +225,24 @@ cudaError_t launch_warp(const ldpc535_code *c, const DecodeParams &p, cudaStream
 }
 
 template <int METHOD, int DC, int DV, bool DBG>
-cudaError_t launch_block(const ldpc535_code *c, const DecodeParams &p, cudaStream_t st)
+cudaError_t launch_block(const ldpc535_code *c, DecodeParams p, cudaStream_t st)
 {
     auto kern = decode_block_kernel<METHOD, DC, DV, DBG>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->block_smem);
+    // shared memory of this method's message type; adjacency tables are staged when they fit
+    const size_t fixed = block_smem_fixed_bytes(DC, c->t.M, c->t.N, (int)sizeof(msg_t<METHOD>));
+    const size_t staged = fixed + c->tabA_bytes + c->tabB_bytes;
+    size_t smem;
+    if (staged <= c->smem_optin) { p.stage_tables = 1; smem = staged; }
+    else if (fixed <= c->smem_optin) { p.stage_tables = 0; smem = fixed; }
+    else return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, c->block_threads, c->block_smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, c->block_threads, smem);
     if (e != cudaSuccess) return e;
     per_sm = std::max(per_sm, 1);
     const int grid = (int)std::min<long long>(p.n_win, (long long)c->sm_count * per_sm);
-    kern<<<grid, c->block_threads, c->block_smem, st>>>(p);
+    kern<<<grid, c->block_threads, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -89,24 +89,29 @@ __device__ __forceinline__ void check_node_spa(float (&m)[DC])
 // Min-sum check update (decodeLogDomainSimple, lib/ldpc_decoder_cb_impl.cc:349-376):
 //     Lr_ji = (prod_k sign(Lq_jk)) * sign(Lq_ji) * min_{k != i} |Lq_jk|,  sign(0) = 0.
 // Padded slots hold +inf (sign +1, never the minimum).
-template <int DC>
-__device__ __forceinline__ void check_node_minsum(float (&m)[DC])
+//
+// Min-sum runs in fp64 (T = double) like the reference: its only operations are +, -, min and
+// sign, all exactly rounded in IEEE arithmetic and kept in the reference's order, so the
+// messages -- not just the decisions -- equal the reference's bit for bit at any iteration
+// count.  (An fp32 min-sum drifts on non-converging frames after a few dozen iterations.)
+template <int DC, typename T>
+__device__ __forceinline__ void check_node_minsum(T (&m)[DC])
 {
-    float min1 = __int_as_float(0x7f800000), min2 = min1;   // two smallest magnitudes
+    T min1 = (T)__int_as_float(0x7f800000), min2 = min1;   // two smallest magnitudes
     int arg1 = -1;
     int prod = 1;
 #pragma unroll
     for (int s = 0; s < DC; s++) {
-        const float a = fabsf(m[s]);
-        prod *= (m[s] > 0.f) - (m[s] < 0.f);
+        const T a = m[s] < (T)0 ? -m[s] : m[s];
+        prod *= (m[s] > (T)0) - (m[s] < (T)0);
         if (a < min1) { min2 = min1; min1 = a; arg1 = s; }
         else if (a < min2) { min2 = a; }
     }
 #pragma unroll
     for (int s = 0; s < DC; s++) {
-        const int sg = prod * ((m[s] > 0.f) - (m[s] < 0.f));
-        const float mn = (s == arg1) ? min2 : min1;
-        m[s] = (float)sg * mn;
+        const int sg = prod * ((m[s] > (T)0) - (m[s] < (T)0));
+        const T mn = (s == arg1) ? min2 : min1;
+        m[s] = (T)sg * mn;
     }
 }
 
@@ -139,13 +144,13 @@ __device__ __forceinline__ float var_node_spa(float (&x)[DV], int dv, float r)
 
 // Min-sum variable update (lib/ldpc_decoder_cb_impl.cc:378-403):
 //   sum = Lr_0 + Lr_1 + ... ;  Lq_k = (Lc + sum) - Lr_k ;  LQ = Lc + sum.
-template <int DV>
-__device__ __forceinline__ float var_node_minsum(float (&x)[DV], int dv, float lc)
+template <int DV, typename T>
+__device__ __forceinline__ T var_node_minsum(T (&x)[DV], int dv, T lc)
 {
-    float sum = 0.f;
+    T sum = (T)0;
 #pragma unroll
-    for (int k = 0; k < DV; k++) sum += (k < dv) ? x[k] : 0.f;
-    const float LQ = lc + sum;
+    for (int k = 0; k < DV; k++) sum += (k < dv) ? x[k] : (T)0;
+    const T LQ = lc + sum;
 #pragma unroll
     for (int k = 0; k < DV; k++) x[k] = LQ - x[k];
     return LQ;
