@@ -94,14 +94,35 @@ __device__ __forceinline__ void static_for(F &&f)
     static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<F &&>(f));
 }
 
-// Occupancy: 12 warps per SM (3 per scheduler, so the four schedulers carry equal work) as
-// three 128-thread CTAs.  The first kSmemEdges messages of a thread live in its shared-memory
-// column (576 B per thread, 216 KB per SM), the remaining kRegEdges in registers; accesses are
-// volatile so the compiler issues real LDS/STS instead of forwarding all 168 values through
-// registers and spilling them to local memory.
-constexpr int kThreads = 128;
-constexpr int kCtasPerSm = 3;
-constexpr int kRegEdges = 24;
+// Occupancy and storage (measured on B200, profiles/): ONE 256-thread CTA per SM, 2 warps per
+// scheduler.  A thread keeps its 64 intrinsic values and kRegEdges of its 168 messages in
+// registers (255 per thread) and the other kSmemEdges in its private shared-memory column.
+// Shared-memory accesses and MUFU share the MIO instruction queue, which was the top stall
+// with all messages in shared memory (384 threads: 1.03e12 edge-iterations/s; this split:
+// 1.13e12).  Phase fences (empty asm with a memory clobber) make the compiler re-read the
+// shared-memory messages at phase boundaries instead of carrying all 168 in registers and
+// spilling them to local memory.
+#ifndef C4_THREADS
+#define C4_THREADS 256
+#endif
+constexpr int kThreads = C4_THREADS;
+constexpr int kCtasPerSm = 1;
+// The unrolled iteration body is ~55 KB of SASS, more than the 32 KB L1.5 instruction cache:
+// twelve warps streaming it independently stall on instruction fetch (ncu: no_instruction was
+// the top stall).  A CTA barrier every few nodes keeps all warps of the SM within one
+// cache-resident window of the code, so each line is fetched once per SM per pass.
+#ifndef C4_CHK_GROUP
+#define C4_CHK_GROUP 8
+#endif
+#ifndef C4_VAR_GROUP
+#define C4_VAR_GROUP 16
+#endif
+constexpr int kChkGroup = C4_CHK_GROUP;     // checks between barriers
+constexpr int kVarGroup = C4_VAR_GROUP;     // variables between barriers
+#ifndef C4_REG_EDGES
+#define C4_REG_EDGES 80
+#endif
+constexpr int kRegEdges = C4_REG_EDGES;
 constexpr int kSmemEdges = kE - kRegEdges;
 constexpr size_t kSmemBytes = (size_t)kThreads * kSmemEdges * sizeof(float);
 
@@ -111,7 +132,7 @@ decode_c4_thread_kernel(const DecodeParams p)
 {
     extern __shared__ float c4_smem[];
     constexpr int NT = kThreads;
-    volatile float *ms = c4_smem + threadIdx.x;
+    float *ms = c4_smem + threadIdx.x;
     float mreg[kRegEdges];
     auto msg_ld = [&](auto ec) -> float {
         constexpr int e = decltype(ec)::value;
@@ -123,10 +144,14 @@ decode_c4_thread_kernel(const DecodeParams p)
     };
     const long long stride = (long long)gridDim.x * NT;
 
-    for (long long w = (long long)blockIdx.x * NT + threadIdx.x; w < p.n_win; w += stride) {
-        const long long off = p.win_offset ? p.win_offset[w] : w * (long long)kN;
-        const float npol = p.polarity ? -(float)p.polarity[w] : -1.f;
-        const bool ok = off >= 0 && off + kN <= p.n_sym;
+    // every thread of the CTA makes the same number of trips (barriers inside); threads past
+    // the end of the batch compute on zeros and store nothing
+    for (long long base = (long long)blockIdx.x * NT; base < p.n_win; base += stride) {
+        const long long w = base + threadIdx.x;
+        const bool live = w < p.n_win;
+        const long long off = !live ? -1 : (p.win_offset ? p.win_offset[w] : w * (long long)kN);
+        const float npol = (live && p.polarity) ? -(float)p.polarity[w] : -1.f;
+        const bool ok = live && off >= 0 && off + kN <= p.n_sym;
 
         // ---- r_i = -pol * Re(sym_i)  (lib/ldpc_decoder_cb_impl.cc:149-153, :486) ----
         float r[kN];
@@ -155,9 +180,10 @@ decode_c4_thread_kernel(const DecodeParams p)
             msg_st(ec, r[c]);
         });
 
-        unsigned h0 = 0, h1 = 0;
-        int cnt = 0, iters = p.max_iters;
-        bool broke = false;
+        asm volatile("" ::: "memory");
+        unsigned h0 = 0, h1 = 0, out_h1 = 0;
+        int cnt = 0, out_cnt = 0, iters = p.max_iters;
+        bool broke = false;          // this codeword's test passed: its outputs are frozen
         for (int h = 0; h < p.max_iters; h++) {
             // ---- Step 1: check messages, in place (:503-516) ----
             static_for<kM>([&](auto jc) {
@@ -169,7 +195,7 @@ decode_c4_thread_kernel(const DecodeParams p)
                     constexpr int s = decltype(sc)::value;
                     m[s] = msg_ld(std::integral_constant<int, a + s>{});
                 });
-                if (DEBUG && p.dbgM) {
+                if (DEBUG && p.dbgM && live && !broke) {
 #pragma unroll
                     for (int s = 0; s < d; s++) p.dbgM[w * kE + a + s] = m[s];
                 }
@@ -178,11 +204,17 @@ decode_c4_thread_kernel(const DecodeParams p)
                     constexpr int s = decltype(sc)::value;
                     msg_st(std::integral_constant<int, a + s>{}, m[s]);
                 });
-                if (DEBUG && p.dbgE) {
+                if (DEBUG && p.dbgE && live && !broke) {
 #pragma unroll
                     for (int s = 0; s < d; s++) p.dbgE[w * kE + a + s] = m[s];
                 }
+                if constexpr (j % kChkGroup == kChkGroup - 1) __syncthreads();
             });
+            // Phase fence (compiler only): messages written above are re-read from shared
+            // memory below instead of being carried in registers across the phase -- inside a
+            // phase every address is a distinct compile-time constant, so the scheduler is
+            // free to interleave the independent nodes.
+            asm volatile("" ::: "memory");
             // ---- Test (:519-532) fused with Step 2 (:540-553) ----
             h0 = 0; h1 = 0;
             static_for<kN>([&](auto ic) {
@@ -204,10 +236,12 @@ decode_c4_thread_kernel(const DecodeParams p)
                         msg_st(std::integral_constant<int, e>{}, x[k]);
                     });
                 }
-                if (DEBUG && p.dbgL) p.dbgL[w * kN + i] = L;
+                if (DEBUG && p.dbgL && live && !broke) p.dbgL[w * kN + i] = L;
                 const unsigned bit = (L <= 0.f) ? 1u : 0u;          // :527
                 if constexpr (i < 32) h0 |= bit << i; else h1 |= bit << (i - 32);
+                if constexpr (i % kVarGroup == kVarGroup - 1) __syncthreads();
             });
+            asm volatile("" ::: "memory");
             // ---- Finished? (:535-537): every iteration, the last included ----
             if (p.early_stop || h + 1 == p.max_iters) {
                 cnt = 0;
@@ -216,10 +250,16 @@ decode_c4_thread_kernel(const DecodeParams p)
                     constexpr unsigned lo = kT.row_lo[j], hi = kT.row_hi[j];
                     cnt += __popc((h0 & lo) ^ (h1 & hi)) & 1;
                 });
-                if (p.early_stop && cnt == 0) { iters = h + 1; broke = true; break; }
+                if (!broke) { out_h1 = h1; out_cnt = cnt; }
+                if (p.early_stop) {
+                    // A converged codeword stops here in the reference; its thread keeps pace
+                    // with the CTA (barriers) but its outputs no longer change.
+                    if (!broke && cnt == 0) { iters = h + 1; broke = true; }
+                    if (__syncthreads_and(broke || !live)) break;
+                }
             }
         }
-        if (DEBUG && p.dbgM && !broke) {
+        if (DEBUG && p.dbgM && live && !broke) {
             static_for<kE>([&](auto ec) {
                 constexpr int e = decltype(ec)::value;
                 p.dbgM[w * kE + e] = msg_ld(ec);
@@ -228,11 +268,11 @@ decode_c4_thread_kernel(const DecodeParams p)
 
         // ---- outputs: bits 32..63 MSB first (:207-219), checkFrame weight (:236-253) ----
         if (ok) {
-            const unsigned bytes = __byte_perm(__brev(h1), 0, 0x0123);
+            const unsigned bytes = __byte_perm(__brev(out_h1), 0, 0x0123);
             *reinterpret_cast<unsigned *>(p.out_bytes + w * 4) = bytes;
-            if (p.out_synd) p.out_synd[w] = (uint8_t)min(cnt, p.thr + 1);
+            if (p.out_synd) p.out_synd[w] = (uint8_t)min(out_cnt, p.thr + 1);
             if (p.out_iters) p.out_iters[w] = (uint8_t)min(iters, 255);
-        } else {
+        } else if (live) {
             *reinterpret_cast<unsigned *>(p.out_bytes + w * 4) = 0u;
             if (p.out_synd) p.out_synd[w] = 255;
             if (p.out_iters) p.out_iters[w] = 255;

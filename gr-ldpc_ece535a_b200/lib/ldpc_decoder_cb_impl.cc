@@ -1,0 +1,179 @@
+/* -*- c++ -*- */
+/*
+ * ldpc_decoder_cb: GNU Radio block, gr_complex in, unsigned char out.
+ *
+ * Behaviour follows the reference block (lib/ldpc_decoder_cb_impl.cc:35-234): 64 symbols per
+ * frame, only the real part is used, the hard-wired 32x64 code, 5 iterations, frames with at
+ * most M/8 = 4 unsatisfied checks are accepted, the OUT_OF_SYNC / IN_SYNC / IN_SYNC_INVERTED
+ * machine slides one symbol at a time while searching, and the 32 data bits leave as 4 bytes
+ * MSB first.  What differs is where the arithmetic runs: windows are decoded in batches by the
+ * sm_100a kernels behind ldpc535_decode_batch (include/ldpc535.h); sync_replay.h explains why
+ * batching cannot change the output.  No CPU decoder exists here: if the GPU library fails the
+ * constructor throws and general_work() returns WORK_DONE.
+ */
+#ifdef HAVE_CONFIG_H
+#include "config.h"
+#endif
+
+#include "ldpc_decoder_cb_impl.h"
+
+#include <gnuradio/io_signature.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+
+namespace gr {
+namespace ldpc_ece535a {
+
+namespace {
+int device_from_env()
+{
+    const char *s = std::getenv("LDPC535_DEVICE");
+    return s ? std::atoi(s) : 0;
+}
+// How far the batcher speculates on a miss.
+const long kTrackBatch = 1 << 16;   // frames at the frame stride
+const long kSearchBatch = 64;       // offsets, each in both polarities
+}  // namespace
+
+ldpc_decoder_cb::sptr ldpc_decoder_cb::make(const int method)
+{
+    return gnuradio::get_initial_sptr(new ldpc_decoder_cb_impl(method));
+}
+
+ldpc_decoder_cb_impl::ldpc_decoder_cb_impl(const int method)
+    : gr::block("ldpc_decoder_cb", gr::io_signature::make(1, 1, sizeof(gr_complex)),
+                gr::io_signature::make(1, 1, sizeof(unsigned char))),
+      d_method(method), d_M(0), d_N(0), d_nbytes(0), d_iterations(LDPC535_REF_ITERATIONS),
+      d_early_stop(true), d_threshold(0), d_code(NULL), d_in(NULL), d_ninput(0), d_max_frames(0),
+      d_base(0), d_stride(1), d_count(0), d_pol_mask(0), d_batches(0), d_windows(0)
+{
+    const int st = ldpc535_code_create_default(device_from_env(), &d_code);
+    if (st != LDPC535_OK)
+        throw std::runtime_error(std::string("ldpc_decoder_cb: cannot set up the GPU decoder: ") +
+                                 ldpc535_strerror(st) + " (" + ldpc535_last_error() + ")");
+    int K = 0;
+    ldpc535_code_info(d_code, &d_M, &d_N, &K, NULL, NULL);
+    d_nbytes = K / 8;
+    d_threshold = d_M / 8;
+
+    // same console line as the reference constructor (:108-116)
+    if (d_method == 3) std::cout << "Decoding method: Hard Decision" << std::endl;
+    else if (d_method == 2) std::cout << "Decoding method: Bit Flipping" << std::endl;
+    else if (d_method == 1) std::cout << "Decoding method: Sum Product" << std::endl;
+    else std::cout << "Decoding method: Log Domain Simple" << std::endl;
+
+    // One output byte needs 16 input symbols; whole frames only.  Hints for the scheduler's
+    // buffer sizing, they do not change what is produced.
+    set_output_multiple(d_nbytes);
+    set_relative_rate((double)d_nbytes / (double)d_N);
+}
+
+ldpc_decoder_cb_impl::~ldpc_decoder_cb_impl() { ldpc535_code_destroy(d_code); }
+
+void ldpc_decoder_cb_impl::forecast(int noutput_items, gr_vector_int &ninput_items_required)
+{
+    // the reference asks for noutput_items * N (:126-130); a frame of N symbols yields
+    // N/16 bytes, so that request is kept (it over-asks, which only helps batching)
+    ninput_items_required[0] = noutput_items * d_N;
+}
+
+void ldpc_decoder_cb_impl::fetch(long offset, int polarity, bool tracking)
+{
+    d_off.clear();
+    d_pol.clear();
+    d_base = offset;
+    if (tracking) {
+        long n = (d_ninput - offset) / d_N;
+        n = std::min(n, std::min(d_max_frames, kTrackBatch));
+        n = std::max(n, 1L);
+        d_stride = d_N;
+        d_count = n;
+        d_pol_mask = polarity > 0 ? 1 : 2;
+        for (long k = 0; k < n; k++) {
+            d_off.push_back(offset + k * d_N);
+            d_pol.push_back((int8_t)polarity);
+        }
+    } else {
+        long n = d_ninput - d_N - offset + 1;       // windows that still fit the input
+        n = std::max(1L, std::min(n, kSearchBatch));
+        d_stride = 1;
+        d_count = n;
+        d_pol_mask = 3;
+        for (int p = 0; p < 2; p++)
+            for (long k = 0; k < n; k++) {
+                d_off.push_back(offset + k);
+                d_pol.push_back((int8_t)(p == 0 ? 1 : -1));
+            }
+    }
+    const size_t nw = d_off.size();
+    d_bytes.resize(nw * (size_t)d_nbytes);
+    d_synd.resize(nw);
+    const int st = ldpc535_decode_batch(d_code, d_in, (size_t)d_ninput, d_off.data(), d_pol.data(), nw,
+                                        d_method, d_iterations, d_early_stop ? 1 : 0, d_threshold,
+                                        d_bytes.data(), d_synd.data(), NULL);
+    if (st != LDPC535_OK)
+        throw std::runtime_error(std::string("ldpc_decoder_cb: GPU decode failed: ") +
+                                 ldpc535_strerror(st) + " (" + ldpc535_last_error() + ")");
+    d_batches++;
+    d_windows += nw;
+}
+
+window_result ldpc_decoder_cb_impl::get(long offset, int polarity, bool tracking)
+{
+    const int bit = polarity > 0 ? 1 : 2;
+    long k = -1;
+    if (d_count > 0 && (d_pol_mask & bit) && offset >= d_base && (offset - d_base) % d_stride == 0) {
+        k = (offset - d_base) / d_stride;
+        if (k >= d_count) k = -1;
+    }
+    if (k < 0) {
+        fetch(offset, polarity, tracking);
+        k = 0;
+    }
+    const size_t idx = (d_pol_mask == 3 && polarity < 0) ? (size_t)(d_count + k) : (size_t)k;
+    window_result r;
+    r.bytes = d_bytes.data() + idx * (size_t)d_nbytes;
+    r.synd = d_synd[idx];
+    return r;
+}
+
+int ldpc_decoder_cb_impl::general_work(int noutput_items, gr_vector_int &ninput_items,
+                                       gr_vector_const_void_star &input_items,
+                                       gr_vector_void_star &output_items)
+{
+    const gr_complex *in = (const gr_complex *)input_items[0];
+    unsigned char *out = (unsigned char *)output_items[0];
+
+    d_in = reinterpret_cast<const float *>(in);
+    d_ninput = ninput_items[0];
+    d_max_frames = noutput_items / d_nbytes;
+    d_count = 0;                                    // results never outlive the input buffer
+
+    long consumed = 0;
+    int produced = 0;
+    try {
+        produced = d_sync.run(*this, d_ninput, noutput_items, d_N, d_nbytes, d_threshold, out,
+                              &consumed, [this](int ev) {
+                                  d_events.push_back(ev);
+                                  if (ev == EV_IN_SYNC) std::cout << "IN SYNC" << std::endl;
+                                  else if (ev == EV_IN_SYNC_INVERTED)
+                                      std::cout << "IN SYNC; PHASE INVERTED" << std::endl;
+                                  else std::cout << "MAX ERRORS; OUT OF SYNC" << std::endl;
+                              });
+    } catch (const std::exception &e) {
+        std::cerr << e.what() << std::endl;         // no CPU fallback: stop the flowgraph
+        return WORK_DONE;
+    }
+    d_in = NULL;
+
+    // Tell runtime system how many input items we consumed and how many we produced.
+    consume_each((int)consumed);
+    return produced;
+}
+
+}  // namespace ldpc_ece535a
+}  // namespace gr

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "libldpc535.so"))
+LIB_PATH = os.environ.get("LDPC535_LIB") or os.path.normpath(os.path.join(_PKG, "..", "..", "libldpc535.so"))
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_SINGULAR, ERR_UNSUPPORTED, ERR_NOMEM = range(7)
 

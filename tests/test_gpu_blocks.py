@@ -1,0 +1,118 @@
+"""GPU: the two GNU Radio blocks, driven through general_work() the way the scheduler does
+(lib/block_harness.cc), against the block-level oracle
+(lib/ldpc_encoder_bc_impl.cc:118-178, lib/ldpc_decoder_cb_impl.cc:132-234 restated in
+oracle/ldpc_oracle.c).  Byte streams, consumed counts, sync events and final sync state must
+be identical; the decoder's windows run on the sm_100a kernels in speculative batches."""
+import numpy as np
+import pytest
+
+import ldpc_ece535a as L
+from ldpc_ece535a import blocks as B
+from oracle import oracle as O
+import util
+from test_sync_replay import make_stream, N, NB
+
+pytestmark = pytest.mark.gpu
+
+
+def test_block_identity_and_forecast():
+    enc, dec = L.ldpc_encoder_bc(), L.ldpc_decoder_cb(1)
+    assert enc.name() == "ldpc_encoder_bc" and dec.name() == "ldpc_decoder_cb"
+    assert enc.item_sizes() == (1, 8)            # unsigned char in, gr_complex out
+    assert dec.item_sizes() == (8, 1)            # gr_complex in, unsigned char out
+    assert enc.forecast(64) == 4 and enc.forecast(65) == 5      # ceil(n / 16)
+    assert dec.forecast(4) == 256                               # noutput_items * 64
+
+
+@pytest.mark.parametrize("nbytes_in,nout", [(4000, 64000), (4003, 64000), (4000, 6400 + 63), (3, 64),
+                                            (4, 63), (0, 640), (40, 0)])
+def test_encoder_block_vs_oracle(shipped, nbytes_in, nout):
+    rng = np.random.default_rng(nbytes_in + nout)
+    data = rng.integers(0, 256, nbytes_in).astype(np.uint8)
+    enc = L.ldpc_encoder_bc()
+    out, consumed = enc.general_work(data, nout)
+    want, wconsumed = O.encoder_work(shipped["Hp"], shipped["L"], shipped["U"], data, nout)
+    assert consumed == wconsumed
+    assert np.array_equal(out, want)
+
+
+CASES = [
+    dict(n_frames=200, ebn0=None, seed=11),
+    dict(n_frames=120, ebn0=None, seed=12, lead=7, invert=True),
+    dict(n_frames=300, ebn0=6.0, seed=13, lead=13),
+    dict(n_frames=300, ebn0=4.0, seed=14, lead=5, burst=(50, 90)),
+    dict(n_frames=200, ebn0=2.0, seed=15, invert=True, lead=70),
+    dict(n_frames=150, ebn0=0.0, seed=16),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("method", [1, 0, 2, 3])
+def test_decoder_block_vs_oracle(shipped, case, method):
+    stream, _ = make_stream(shipped, **case)
+    noutput = (stream.size // N) * NB
+    dec = L.ldpc_decoder_cb(method)
+    got, consumed = dec.general_work(stream, noutput)
+    blk = O.DecoderBlock(shipped["Hp"], method)
+    want, wconsumed = blk.work(stream, noutput)
+    assert consumed == wconsumed
+    assert np.array_equal(got, want)
+    assert dec.take_events() == blk.events
+    st = dec.state()
+    assert (st["state"], st["errors"]) == (blk.st.state, blk.st.errors)
+    assert st["gpu_windows"] >= consumed // N       # everything was decoded on the GPU
+
+
+def test_decoder_block_chunked_like_the_scheduler(shipped):
+    """Small, irregular work calls (GNU Radio's default buffers hold ~64 frames): unconsumed
+    symbols come back in the next call, output space is sometimes short."""
+    stream, data = make_stream(shipped, n_frames=400, ebn0=5.0, seed=21, lead=33, burst=(100, 140))
+    blk = O.DecoderBlock(shipped["Hp"], 1)
+    want, _ = blk.work(stream, 400 * NB)
+    dec = L.ldpc_decoder_cb(1)
+    rng = np.random.default_rng(1)
+    got, pos = [], 0
+    while stream.size - pos >= N:
+        take = int(rng.integers(N, 4096))
+        nout = int(rng.integers(0, 64)) * NB + int(rng.integers(0, 4))
+        out, consumed = dec.general_work(stream[pos:pos + take], nout)
+        got += list(out)
+        pos += consumed
+        if consumed == 0 and take >= stream.size - pos and nout >= NB:
+            break
+    assert got == list(want)
+    assert dec.take_events() == blk.events
+
+
+def test_transmit_receive_pipeline(shipped):
+    """BASELINE config 2's shape: an image-sized byte file (19 270 bytes, as examples/mandril.bmp)
+    through encoder block -> AWGN -> decoder block at Eb/N0 = 0..4 dB; at every SNR the decoded
+    stream equals the block-level oracle's, and the noiseless run returns the file."""
+    rng = np.random.default_rng(31)
+    payload = rng.integers(0, 256, 19270).astype(np.uint8)
+    payload[:2] = (0x42, 0x4D)                               # 'BM'
+    enc = L.ldpc_encoder_bc()
+    sym, consumed = enc.general_work(payload, (payload.size // 4) * 64)
+    assert consumed == 19268 and sym.size == 4817 * 64       # two tail bytes never encoded
+    dec = L.ldpc_decoder_cb(1)
+    out, c = dec.general_work(sym, 4817 * 4)
+    assert np.array_equal(out, payload[:19268]) and c == sym.size
+    for ebn0 in (0.0, 1.0, 2.0, 3.0, 4.0):
+        noisy = util.awgn(sym, ebn0, np.random.default_rng(int(ebn0) + 40))
+        dec = L.ldpc_decoder_cb(1)
+        got, consumed = dec.general_work(noisy, 4817 * 4)
+        blk = O.DecoderBlock(shipped["Hp"], 1)
+        want, wconsumed = blk.work(noisy, 4817 * 4)
+        assert consumed == wconsumed and np.array_equal(got, want), ebn0
+        assert dec.take_events() == blk.events
+
+
+def test_decoder_block_iteration_knob(shipped):
+    """max_iterations / early_stop are additions; the defaults are the reference's 5 / on."""
+    stream, _ = make_stream(shipped, n_frames=100, ebn0=3.0, seed=51)
+    dec = L.ldpc_decoder_cb(1)
+    dec.set_max_iterations(50, early_stop=True)
+    got, consumed = dec.general_work(stream, 400)
+    blk = O.DecoderBlock(shipped["Hp"], 1, iterations=50)
+    want, wconsumed = blk.work(stream, 400)
+    assert consumed == wconsumed and np.array_equal(got, want)
