@@ -315,7 +315,12 @@ def run_gpu(args):
         xu_peak_ops = SM_COUNT * XU_LANES * f_max
         roofline = {
             "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": hbm_achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": hbm_achieved / hbm_peak,
+            # ncu --set full, dram__bytes_read+write of this kernel: 523.2 B per codeword
+            # (profiles/r1_kernels_ncu_full.txt) against 518 B algorithmic
+            "traffic": n_cw * 523.2 if code.kernel_name(L.METHOD_SUMPRODUCT) == "c4-thread" else None,
+            "traffic_unit": "bytes per launch", "algorithmic_bytes": n_cw * BYTES_PER_CW,
+            "peak_source": peak_src,
             "kernel": code.kernel_name(L.METHOD_SUMPRODUCT), "kernel_ms": kern_ms,
             "note": "a fixed-50-iteration sum-product is bound by the SM special-function/issue "
                     "pipes, not HBM (SURVEY 8d); `governing` is the roofline that applies",
@@ -329,8 +334,8 @@ def run_gpu(args):
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config(n_cw, world),
-                "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": n_cw * 512,
-                        "d2h_bytes_per_step": n_cw * 6, "steps": e2e_steps,
+                "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": n_cw * world * 512,
+                        "d2h_bytes_per_step": n_cw * world * 6, "steps": e2e_steps,
                         "ms_per_step": e2e_ms / e2e_steps,
                         "api": "ldpc535_decode_batch (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)",
                         "matches_device_path": e2e_same},
