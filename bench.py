@@ -298,6 +298,10 @@ def run_gpu(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = n_cw * world * e2e_steps * K_INFO / (e2e_ms * 1e-3) / 1e9
     e2e_same = bool(np.array_equal(h_bytes, d_bytes.cpu().numpy()))
+    hp = code.host_path()
+    host_path = ("%d host threads pack the real parts into pinned staging (halves PCIe bytes)" % hp["pack_threads"]
+                 if hp["pack_pinned"] else "copy engine reads the caller's pinned buffer directly")
+    pcie_bytes = n_cw * world * (256 if hp["pack_pinned"] else 512)
 
     if rank == 0:
         peaks = {}
@@ -337,7 +341,8 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": n_cw * world * 512,
                         "d2h_bytes_per_step": n_cw * world * 6, "steps": e2e_steps,
                         "ms_per_step": e2e_ms / e2e_steps,
-                        "api": "ldpc535_decode_batch (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)",
+                        "api": "ldpc535_decode_batch (pinned host buffers, 3-slot stage/H2D/kernel/D2H pipeline)",
+                        "host_path": host_path, "pcie_h2d_bytes_per_step": pcie_bytes,
                         "matches_device_path": e2e_same},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "check": {"frames_recovered": frame_ok, "frames_not_at_max_iters": bad_iters}}

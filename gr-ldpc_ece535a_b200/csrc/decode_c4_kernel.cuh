@@ -155,7 +155,21 @@ decode_c4_thread_kernel(const DecodeParams p)
 
         // ---- r_i = -pol * Re(sym_i)  (lib/ldpc_decoder_cb_impl.cc:149-153, :486) ----
         float r[kN];
-        if (ok) {
+        if (ok && p.sym_re) {
+            const float *s = p.sym_re + off;
+            if ((off & 3) == 0) {
+                const float4 *s4 = reinterpret_cast<const float4 *>(s);
+#pragma unroll
+                for (int i = 0; i < kN / 4; i++) {
+                    const float4 v = __ldg(s4 + i);
+                    r[4 * i] = npol * v.x; r[4 * i + 1] = npol * v.y;
+                    r[4 * i + 2] = npol * v.z; r[4 * i + 3] = npol * v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kN; i++) r[i] = npol * __ldg(s + i);
+            }
+        } else if (ok) {
             const float2 *s = p.sym + off;
             if ((off & 1) == 0) {
                 const float4 *s4 = reinterpret_cast<const float4 *>(s);

@@ -18,7 +18,8 @@ namespace ldpc535 {
 enum { kMethodMinSum = 0, kMethodSpa = 1, kMethodBitFlip = 2, kMethodHard = 3 };
 
 struct DecodeParams {
-    const float2 *sym;            // complex symbols
+    const float2 *sym;            // complex symbols (re, im) ...
+    const float *sym_re;          // ... or, when non-null, real parts only (host-packed staging)
     long long n_sym;
     const long long *win_offset;  // or nullptr: window w starts at w * N
     const signed char *polarity;  // or nullptr: +1
@@ -49,6 +50,12 @@ __host__ __device__ inline size_t block_smem_fixed_bytes(int dc, int M, int N, i
     return (b + 15) & ~(size_t)15;
 }
 constexpr float kInf = __builtin_huge_valf();
+
+// Re(symbol i) of either input layout
+__device__ __forceinline__ float load_re(const DecodeParams &p, long long i)
+{
+    return p.sym_re ? __ldg(p.sym_re + i) : __ldg(&p.sym[i].x);
+}
 
 // message type of a method: fp64 for min-sum (exact, see spa_math.cuh), fp32 otherwise
 template <int METHOD>
@@ -113,7 +120,7 @@ decode_warp_kernel(const DecodeParams p)
 #pragma unroll
         for (int t = 0; t < 2; t++) {
             const int v = lane + 32 * t;
-            r[t] = (T)((ok && v < N) ? -pol * __ldg(&p.sym[off + v].x) : 0.f);
+            r[t] = (T)((ok && v < N) ? -pol * load_re(p, off + v) : 0.f);
         }
         uint32_t hard0 = 0, hard1 = 0, bad = 0;
         int iters = 0;
@@ -297,7 +304,7 @@ decode_block_kernel(const DecodeParams p)
         const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
         const bool ok = off >= 0 && off + N <= p.n_sym;
         __syncthreads();                                   // previous window fully drained
-        for (int i = tid; i < N; i += nt) r[i] = ok ? -pol * __ldg(&p.sym[off + i].x) : 0.f;
+        for (int i = tid; i < N; i += nt) r[i] = ok ? -pol * load_re(p, off + i) : 0.f;
         if (tid == 0) red[0] = 0;
         __syncthreads();
 

@@ -33,6 +33,7 @@ SYMBOLS = {
     "ldpc535_code_kernel_name": (C.c_char_p, [_vp, _i]),
     "ldpc535_code_set_kernel": (_i, [_vp, C.c_char_p]),
     "ldpc535_launch_count": (_u64, [_vp]),
+    "ldpc535_code_host_path": (_i, [_vp, _pi, _pi]),
     "ldpc535_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "ldpc535_host_free": (_i, [_vp]),
     "ldpc535_encode_batch": (_i, [_vp, _vp, _sz, _vp]),

@@ -84,6 +84,12 @@ class Code:
         check(lib().ldpc535_code_set_kernel(self._h, None if name is None else name.encode()),
               "set_kernel")
 
+    def host_path(self):
+        """How decode() moves host symbols: {'pack_pinned': bool, 'pack_threads': int}."""
+        a, b = C.c_int(), C.c_int()
+        check(lib().ldpc535_code_host_path(self._h, a, b), "host_path")
+        return {"pack_pinned": bool(a.value), "pack_threads": b.value}
+
     def launch_count(self):
         return int(lib().ldpc535_launch_count(self._h))
 

@@ -193,6 +193,14 @@ LDPC535_API int ldpc535_decode_debug(ldpc535_code *code, const float *sym, size_
  * NULL/"auto" = default).  Returns LDPC535_ERR_UNSUPPORTED if the code cannot run on it. */
 LDPC535_API int ldpc535_code_set_kernel(ldpc535_code *code, const char *kernel);
 
+/* How ldpc535_decode_batch moves host symbols to the device.  Pageable input is always staged
+ * through pinned memory by `pack_threads` host threads that copy only the REAL parts (the
+ * decoder never reads the imaginary ones), halving the PCIe bytes; *pack_pinned != 0 means
+ * pinned input is packed the same way instead of being handed to the copy engine as it is
+ * (default when >= 8 threads are available; LDPC535_PACK_PINNED / LDPC535_PACK_THREADS
+ * override). */
+LDPC535_API int ldpc535_code_host_path(const ldpc535_code *code, int *pack_pinned, int *pack_threads);
+
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 LDPC535_API uint64_t ldpc535_launch_count(const ldpc535_code *code);
 
