@@ -106,7 +106,10 @@ __device__ __forceinline__ void static_for(F &&f)
 #define C4_THREADS 256
 #endif
 constexpr int kThreads = C4_THREADS;
-constexpr int kCtasPerSm = 1;
+#ifndef C4_CTAS
+#define C4_CTAS 1
+#endif
+constexpr int kCtasPerSm = C4_CTAS;
 // The unrolled iteration body is ~55 KB of SASS, more than the 32 KB L1.5 instruction cache:
 // twelve warps streaming it independently stall on instruction fetch (ncu: no_instruction was
 // the top stall).  A CTA barrier every few nodes keeps all warps of the SM within one
@@ -120,11 +123,20 @@ constexpr int kCtasPerSm = 1;
 constexpr int kChkGroup = C4_CHK_GROUP;     // checks between barriers
 constexpr int kVarGroup = C4_VAR_GROUP;     // variables between barriers
 #ifndef C4_REG_EDGES
-#define C4_REG_EDGES 80
+#define C4_REG_EDGES 100
+#endif
+#ifndef C4_GROUPS
+#define C4_GROUPS 1
+#endif
+constexpr int kGroups = C4_GROUPS;          // 1: all warps in lock step; 2, 3: rotated groups
+#ifndef C4_REG_R
+#define C4_REG_R 0
 #endif
 constexpr int kRegEdges = C4_REG_EDGES;
 constexpr int kSmemEdges = kE - kRegEdges;
-constexpr size_t kSmemBytes = (size_t)kThreads * kSmemEdges * sizeof(float);
+constexpr int kRegR = C4_REG_R;             // intrinsic values kept in registers; the rest in smem
+constexpr int kSmemR = kN - kRegR;          // (an r is read once per iteration, a message four times)
+constexpr size_t kSmemBytes = (size_t)kThreads * (kSmemEdges + kSmemR) * sizeof(float);
 
 template <bool DEBUG>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -143,6 +155,13 @@ decode_c4_thread_kernel(const DecodeParams p)
         if constexpr (e < kSmemEdges) ms[e * NT] = v; else mreg[e - kSmemEdges] = v;
     };
     const long long stride = (long long)gridDim.x * NT;
+    // group of this warp: warps [g * W, (g+1) * W) with W = warps / kGroups a multiple of 4, so
+    // every SM sub-partition (warp id mod 4) holds one warp of each group
+    const int grp = (kGroups > 1) ? (int)(threadIdx.x / (NT / kGroups)) : 0;
+    auto group_sync = [&]() {
+        if constexpr (kGroups == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" :: "r"(1 + grp), "n"(NT / kGroups) : "memory");
+    };
 
     // every thread of the CTA makes the same number of trips (barriers inside); threads past
     // the end of the batch compute on zeros and store nothing
@@ -150,7 +169,7 @@ decode_c4_thread_kernel(const DecodeParams p)
         const long long w = base + threadIdx.x;
         const bool live = w < p.n_win;
         const long long off = !live ? -1 : (p.win_offset ? p.win_offset[w] : w * (long long)kN);
-        const float npol = (live && p.polarity) ? -(float)p.polarity[w] : -1.f;
+        const float npol = ((live && p.polarity) ? -(float)p.polarity[w] : -1.f) * kSpaScale;   // units of ln 2
         const bool ok = live && off >= 0 && off + kN <= p.n_sym;
 
         // ---- r_i = -pol * Re(sym_i)  (lib/ldpc_decoder_cb_impl.cc:149-153, :486) ----
@@ -187,21 +206,28 @@ decode_c4_thread_kernel(const DecodeParams p)
 #pragma unroll
             for (int i = 0; i < kN; i++) r[i] = 0.f;
         }
-        // M_ji = r_i on every edge (:489-496)
+        static_for<kSmemR>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            ms[(kSmemEdges + i) * NT] = r[kRegR + i];
+        });
+        // M_ji = r_i on every edge (:489-496), stored as t = copysign(2^-|M|, M)
         static_for<kE>([&](auto ec) {
             constexpr int e = decltype(ec)::value;
             constexpr int c = kT.col_idx[e];
-            msg_st(ec, r[c]);
+            if (DEBUG && p.dbgS && live) p.dbgS[w * kE + e] = r[c] * kSpaUnscale;
+            msg_st(ec, to_check_msg(r[c]));
         });
 
         asm volatile("" ::: "memory");
-        unsigned h0 = 0, h1 = 0, out_h1 = 0;
-        int cnt = 0, out_cnt = 0, iters = p.max_iters;
+        unsigned out_h1 = 0;
+        int out_cnt = 0, iters = p.max_iters;
         bool broke = false;          // this codeword's test passed: its outputs are frozen
-        for (int h = 0; h < p.max_iters; h++) {
-            // ---- Step 1: check messages, in place (:503-516) ----
-            static_for<kM>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
+
+        // ---- Step 1: check messages of checks [J0, J1), in place (:503-516) ----
+        auto check_range = [&](auto j0c, auto j1c) {
+            constexpr int J0 = decltype(j0c)::value, J1 = decltype(j1c)::value;
+            static_for<J1 - J0>([&](auto jc) {
+                constexpr int j = J0 + decltype(jc)::value;
                 constexpr int a = kT.row_ptr[j];
                 constexpr int d = kT.row_ptr[j + 1] - a;
                 float m[d];
@@ -209,9 +235,9 @@ decode_c4_thread_kernel(const DecodeParams p)
                     constexpr int s = decltype(sc)::value;
                     m[s] = msg_ld(std::integral_constant<int, a + s>{});
                 });
-                if (DEBUG && p.dbgM && live && !broke) {
+                if (DEBUG && p.dbgM && live && !broke) {     // M entering this check step
 #pragma unroll
-                    for (int s = 0; s < d; s++) p.dbgM[w * kE + a + s] = m[s];
+                    for (int s = 0; s < d; s++) p.dbgM[w * kE + a + s] = p.dbgS[w * kE + a + s];
                 }
                 check_node_spa<d>(m);
                 static_for<d>([&](auto sc) {
@@ -220,17 +246,14 @@ decode_c4_thread_kernel(const DecodeParams p)
                 });
                 if (DEBUG && p.dbgE && live && !broke) {
 #pragma unroll
-                    for (int s = 0; s < d; s++) p.dbgE[w * kE + a + s] = m[s];
+                    for (int s = 0; s < d; s++) p.dbgE[w * kE + a + s] = m[s] * kSpaUnscale;
                 }
-                if constexpr (j % kChkGroup == kChkGroup - 1) __syncthreads();
+                if constexpr (j % kChkGroup == kChkGroup - 1) group_sync();
             });
-            // Phase fence (compiler only): messages written above are re-read from shared
-            // memory below instead of being carried in registers across the phase -- inside a
-            // phase every address is a distinct compile-time constant, so the scheduler is
-            // free to interleave the independent nodes.
-            asm volatile("" ::: "memory");
-            // ---- Test (:519-532) fused with Step 2 (:540-553) ----
-            h0 = 0; h1 = 0;
+        };
+        // ---- Test (:519-532) fused with Step 2 (:540-553), then Finished? (:535-537) ----
+        auto var_all = [&](int h) {
+            unsigned h0 = 0, h1 = 0;
             static_for<kN>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 constexpr int a = kT.col_ptr[i];
@@ -243,40 +266,71 @@ decode_c4_thread_kernel(const DecodeParams p)
                         constexpr int e = kT.edge_of_col[a + k];
                         x[k] = msg_ld(std::integral_constant<int, e>{});
                     });
-                    L = var_node_spa<dv>(x, dv, r[i]);
+                    float ri;
+                    if constexpr (i < kRegR) ri = r[i]; else ri = ms[(kSmemEdges + i - kRegR) * NT];
+                    L = var_node_spa<dv>(x, dv, ri);
                     static_for<dv>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
                         constexpr int e = kT.edge_of_col[a + k];
-                        msg_st(std::integral_constant<int, e>{}, x[k]);
+                        if (DEBUG && p.dbgS && live && !broke) p.dbgS[w * kE + e] = x[k] * kSpaUnscale;
+                        msg_st(std::integral_constant<int, e>{}, to_check_msg(x[k]));
                     });
                 }
-                if (DEBUG && p.dbgL && live && !broke) p.dbgL[w * kN + i] = L;
+                if (DEBUG && p.dbgL && live && !broke) p.dbgL[w * kN + i] = L * kSpaUnscale;
                 const unsigned bit = (L <= 0.f) ? 1u : 0u;          // :527
                 if constexpr (i < 32) h0 |= bit << i; else h1 |= bit << (i - 32);
-                if constexpr (i % kVarGroup == kVarGroup - 1) __syncthreads();
+                if constexpr (i % kVarGroup == kVarGroup - 1) group_sync();
             });
-            asm volatile("" ::: "memory");
-            // ---- Finished? (:535-537): every iteration, the last included ----
+            // the syndrome is tested every iteration, the last included
             if (p.early_stop || h + 1 == p.max_iters) {
-                cnt = 0;
+                int cnt = 0;
                 static_for<kM>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     constexpr unsigned lo = kT.row_lo[j], hi = kT.row_hi[j];
                     cnt += __popc((h0 & lo) ^ (h1 & hi)) & 1;
                 });
                 if (!broke) { out_h1 = h1; out_cnt = cnt; }
-                if (p.early_stop) {
-                    // A converged codeword stops here in the reference; its thread keeps pace
-                    // with the CTA (barriers) but its outputs no longer change.
-                    if (!broke && cnt == 0) { iters = h + 1; broke = true; }
-                    if (__syncthreads_and(broke || !live)) break;
+                // A converged codeword stops here in the reference; its thread keeps pace with
+                // the CTA (barriers) but its outputs no longer change.
+                if (p.early_stop && !broke && cnt == 0) { iters = h + 1; broke = true; }
+            }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using IH = std::integral_constant<int, kM / 2>;
+        using IM = std::integral_constant<int, kM>;
+
+        // Rotation: the warps of an SM sub-partition belong to different groups, and group g runs
+        // one sub-step behind group g-1, so that while one group is in the MUFU-free variable
+        // phase the others keep the XU pipe busy with check nodes (in lock step all warps hit
+        // the variable phase together and the XU pipe idles ~20 % of the time).
+        const int n_sub = kGroups * p.max_iters;
+        for (int t = 0; t < n_sub + kGroups - 1; t++) {
+            const int u = t - grp;
+            if (u >= 0 && u < n_sub) {
+                const int h = u / kGroups, ph = u - h * kGroups;
+                if constexpr (kGroups == 1) {
+                    check_range(I0{}, IM{});
+                    asm volatile("" ::: "memory");
+                    var_all(h);
+                } else if constexpr (kGroups == 2) {
+                    if (ph == 0) check_range(I0{}, IM{}); else var_all(h);
+                } else {
+                    if (ph == 0) check_range(I0{}, IH{});
+                    else if (ph == 1) check_range(IH{}, IM{});
+                    else var_all(h);
                 }
+            }
+            asm volatile("" ::: "memory");
+            if (p.early_stop) {
+                if (__syncthreads_and(broke || !live)) break;
+            } else if (kGroups > 1) {
+                __syncthreads();
             }
         }
         if (DEBUG && p.dbgM && live && !broke) {
             static_for<kE>([&](auto ec) {
                 constexpr int e = decltype(ec)::value;
-                p.dbgM[w * kE + e] = msg_ld(ec);
+                p.dbgM[w * kE + e] = p.dbgS[w * kE + e];
             });
         }
 

@@ -32,6 +32,8 @@ struct DecodeParams {
     uint8_t *out_bytes, *out_synd, *out_iters;
     // message dumps (DEBUG instantiations only)
     float *dbgL, *dbgE, *dbgM;
+    float *dbgS;                  // scratch [n_win][E]: latest bit->check messages M (the kernels
+                                  // store them as copysign(exp(-|M|), M), see spa_math.cuh)
     const int32_t *slot_edge;     // [DC][M] -> CSR edge id or -1
     // block kernel: table staging
     int stage_tables;             // 1: copy chk_var / var_slot into shared memory
@@ -50,6 +52,19 @@ __host__ __device__ inline size_t block_smem_fixed_bytes(int dc, int M, int N, i
     return (b + 15) & ~(size_t)15;
 }
 constexpr float kInf = __builtin_huge_valf();
+
+// stored form of a bit->check message: sum-product keeps copysign(exp(-|M|), M) (spa_math.cuh),
+// the other methods the message itself; a padded slot holds the identity of the check update
+template <int METHOD, typename T>
+__device__ __forceinline__ T enc_msg(T M)
+{
+    if constexpr (METHOD == kMethodSpa) return to_check_msg(M); else return M;
+}
+template <int METHOD, typename T>
+__device__ __forceinline__ T pad_msg()
+{
+    if constexpr (METHOD == kMethodSpa) return (T)0; else return (T)kInf;
+}
 
 // Re(symbol i) of either input layout
 __device__ __forceinline__ float load_re(const DecodeParams &p, long long i)
@@ -109,18 +124,20 @@ decode_warp_kernel(const DecodeParams p)
     }
 #pragma unroll
     for (int s = 0; s < DC; s++)
-        if (s >= cdeg) msg[s * 32 + lane] = (T)kInf; // padded slots: identity, never rewritten
+        if (s >= cdeg) msg[s * 32 + lane] = pad_msg<METHOD, T>();   // padded slots, never rewritten
 
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w < p.n_win; w += warps_total) {
         const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
         const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
         const bool ok = off >= 0 && off + N <= p.n_sym;
+        constexpr float kIn = (METHOD == kMethodSpa) ? kSpaScale : 1.f;      // SPA works in units of ln 2
+        constexpr float kOut = (METHOD == kMethodSpa) ? kSpaUnscale : 1.f;   // (message dumps only)
         T r[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
             const int v = lane + 32 * t;
-            r[t] = (T)((ok && v < N) ? -pol * load_re(p, off + v) : 0.f);
+            r[t] = (T)((ok && v < N) ? (-pol * kIn) * load_re(p, off + v) : 0.f);
         }
         uint32_t hard0 = 0, hard1 = 0, bad = 0;
         int iters = 0;
@@ -159,7 +176,11 @@ decode_warp_kernel(const DecodeParams p)
             for (int t = 0; t < 2; t++)
 #pragma unroll
                 for (int k = 0; k < DV; k++)
-                    if (k < vdeg[t]) msg[vpos[t][k]] = r[t];
+                    if (k < vdeg[t]) {
+                        if (DEBUG && p.dbgS)
+                            p.dbgS[w * p.E + p.slot_edge[(vpos[t][k] >> 5) * M + (vpos[t][k] & 31)]] = (float)r[t] * kOut;
+                        msg[vpos[t][k]] = enc_msg<METHOD, T>(r[t]);
+                    }
             iters = p.max_iters;
             for (int h = 0; h < p.max_iters; h++) {
                 __syncwarp();
@@ -169,7 +190,10 @@ decode_warp_kernel(const DecodeParams p)
                 if (DEBUG && p.dbgM && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < cdeg) p.dbgM[w * p.E + p.slot_edge[s * M + lane]] = (float)m[s];
+                        if (s < cdeg) {
+                            const long long ei = w * p.E + p.slot_edge[s * M + lane];
+                            p.dbgM[ei] = p.dbgS[ei];             // M entering this check step
+                        }
                 }
                 if constexpr (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC, T>(m);
 #pragma unroll
@@ -178,7 +202,7 @@ decode_warp_kernel(const DecodeParams p)
                 if (DEBUG && p.dbgE && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < cdeg) p.dbgE[w * p.E + p.slot_edge[s * M + lane]] = (float)m[s];
+                        if (s < cdeg) p.dbgE[w * p.E + p.slot_edge[s * M + lane]] = (float)m[s] * kOut;
                 }
                 __syncwarp();
                 T x[2][DV], L[2];
@@ -196,8 +220,8 @@ decode_warp_kernel(const DecodeParams p)
                 hard1 = __ballot_sync(0xffffffffu, b1);
                 bad = __ballot_sync(0xffffffffu, (__popc(row_lo & hard0) + __popc(row_hi & hard1)) & 1);
                 if (DEBUG && p.dbgL) {
-                    if (lane < N) p.dbgL[w * N + lane] = (float)L[0];
-                    if (lane + 32 < N) p.dbgL[w * N + lane + 32] = (float)L[1];
+                    if (lane < N) p.dbgL[w * N + lane] = (float)L[0] * kOut;
+                    if (lane + 32 < N) p.dbgL[w * N + lane + 32] = (float)L[1] * kOut;
                 }
                 // SPA tests every iteration, the last included (:535); min-sum skips the
                 // test on the last one (:406)
@@ -207,7 +231,11 @@ decode_warp_kernel(const DecodeParams p)
                 for (int t = 0; t < 2; t++)
 #pragma unroll
                     for (int k = 0; k < DV; k++)
-                        if (k < vdeg[t]) msg[vpos[t][k]] = x[t][k];
+                        if (k < vdeg[t]) {
+                            if (DEBUG && p.dbgS)
+                                p.dbgS[w * p.E + p.slot_edge[(vpos[t][k] >> 5) * M + (vpos[t][k] & 31)]] = (float)x[t][k] * kOut;
+                            msg[vpos[t][k]] = enc_msg<METHOD, T>(x[t][k]);
+                        }
             }
             // dbgM so far holds the M that ENTERED the last check step -- what the reference
             // still holds after a successful test; without one the last Step 2 counts too.
@@ -216,7 +244,10 @@ decode_warp_kernel(const DecodeParams p)
                 if (lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < cdeg) p.dbgM[w * p.E + p.slot_edge[s * M + lane]] = (float)msg[s * 32 + lane];
+                        if (s < cdeg) {
+                            const long long ei = w * p.E + p.slot_edge[s * M + lane];
+                            p.dbgM[ei] = p.dbgS[ei];
+                        }
                 }
             }
         }
@@ -303,8 +334,10 @@ decode_block_kernel(const DecodeParams p)
         const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
         const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
         const bool ok = off >= 0 && off + N <= p.n_sym;
+        constexpr float kIn = (METHOD == kMethodSpa) ? kSpaScale : 1.f;
+        constexpr float kOut = (METHOD == kMethodSpa) ? kSpaUnscale : 1.f;
         __syncthreads();                                   // previous window fully drained
-        for (int i = tid; i < N; i += nt) r[i] = ok ? -pol * load_re(p, off + i) : 0.f;
+        for (int i = tid; i < N; i += nt) r[i] = ok ? (-pol * kIn) * load_re(p, off + i) : 0.f;
         if (tid == 0) red[0] = 0;
         __syncthreads();
 
@@ -377,7 +410,8 @@ decode_block_kernel(const DecodeParams p)
         } else {
             for (int idx = tid; idx < DC * M; idx += nt) {
                 const int v = chk_var[idx];
-                msg[idx] = (T)((v != 0xFFFF) ? r[v] : kInf);
+                if (DEBUG && p.dbgS && v != 0xFFFF) p.dbgS[w * p.E + p.slot_edge[idx]] = r[v] * kOut;
+                msg[idx] = (v != 0xFFFF) ? enc_msg<METHOD, T>((T)r[v]) : pad_msg<METHOD, T>();
             }
             __syncthreads();
             iters = p.max_iters;
@@ -391,7 +425,10 @@ decode_block_kernel(const DecodeParams p)
                     if (DEBUG && p.dbgM) {
 #pragma unroll
                         for (int s = 0; s < DC; s++)
-                            if (s < deg) p.dbgM[w * p.E + p.slot_edge[s * M + j]] = (float)m[s];
+                            if (s < deg) {
+                                const long long ei = w * p.E + p.slot_edge[s * M + j];
+                                p.dbgM[ei] = p.dbgS[ei];         // M entering this check step
+                            }
                     }
                     if constexpr (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC, T>(m);
 #pragma unroll
@@ -400,7 +437,7 @@ decode_block_kernel(const DecodeParams p)
                     if (DEBUG && p.dbgE) {
 #pragma unroll
                         for (int s = 0; s < DC; s++)
-                            if (s < deg) p.dbgE[w * p.E + p.slot_edge[s * M + j]] = (float)m[s];
+                            if (s < deg) p.dbgE[w * p.E + p.slot_edge[s * M + j]] = (float)m[s] * kOut;
                     }
                 }
                 __syncthreads();
@@ -421,10 +458,13 @@ decode_block_kernel(const DecodeParams p)
                         if constexpr (METHOD == kMethodSpa) L = var_node_spa<DV>(x, dv, r[i]);
                         else L = var_node_minsum<DV, T>(x, dv, (T)r[i]);
                         b = (METHOD == kMethodSpa) ? (L <= (T)0) : (L < (T)0);
-                        if (DEBUG && p.dbgL) p.dbgL[w * N + i] = (float)L;
+                        if (DEBUG && p.dbgL) p.dbgL[w * N + i] = (float)L * kOut;
 #pragma unroll
                         for (int k = 0; k < DV; k++)
-                            if (k < dv) msg[idx[k]] = x[k];
+                            if (k < dv) {
+                                if (DEBUG && p.dbgS) p.dbgS[w * p.E + p.slot_edge[idx[k]]] = (float)x[k] * kOut;
+                                msg[idx[k]] = enc_msg<METHOD, T>(x[k]);
+                            }
                     }
                     const uint32_t wd = __ballot_sync(0xffffffffu, b);
                     if (lane == 0 && i < N) hard[i >> 5] = wd;
@@ -456,7 +496,10 @@ decode_block_kernel(const DecodeParams p)
                     const int deg = p.chk_deg[j];
 #pragma unroll
                     for (int s = 0; s < DC; s++)
-                        if (s < deg) p.dbgM[w * p.E + p.slot_edge[s * M + j]] = (float)msg[s * M + j];
+                        if (s < deg) {
+                            const long long ei = w * p.E + p.slot_edge[s * M + j];
+                            p.dbgM[ei] = p.dbgS[ei];
+                        }
                 }
             }
         }

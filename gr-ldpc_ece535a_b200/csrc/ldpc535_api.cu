@@ -755,11 +755,11 @@ int ldpc535_decode_debug(ldpc535_code *c, const float *sym, size_t n_win, int ma
     DeviceGuard g(c->device);
     NEED_DEVICE(c, g);
     const size_t N = (size_t)c->t.N, E = (size_t)c->t.E, nb = (size_t)(c->t.K + 7) / 8;
-    float *d_sym = nullptr, *dL = nullptr, *dE = nullptr, *dM = nullptr;
+    float *d_sym = nullptr, *dL = nullptr, *dE = nullptr, *dM = nullptr, *dS = nullptr;
     uint8_t *d_bytes = nullptr, *d_iters = nullptr;
     int st = LDPC535_OK;
     auto cleanup = [&]() {
-        cudaFree(d_sym); cudaFree(dL); cudaFree(dE); cudaFree(dM); cudaFree(d_bytes); cudaFree(d_iters);
+        cudaFree(d_sym); cudaFree(dL); cudaFree(dE); cudaFree(dM); cudaFree(dS); cudaFree(d_bytes); cudaFree(d_iters);
     };
 #define CUX(call)                                                                          \
     do {                                                                                   \
@@ -773,19 +773,21 @@ int ldpc535_decode_debug(ldpc535_code *c, const float *sym, size_t n_win, int ma
     CUX(cudaMalloc(reinterpret_cast<void **>(&dL), std::max<size_t>(n_win * N * 4, 4)));
     CUX(cudaMalloc(reinterpret_cast<void **>(&dE), std::max<size_t>(n_win * E * 4, 4)));
     CUX(cudaMalloc(reinterpret_cast<void **>(&dM), std::max<size_t>(n_win * E * 4, 4)));
+    CUX(cudaMalloc(reinterpret_cast<void **>(&dS), std::max<size_t>(n_win * E * 4, 4)));
     CUX(cudaMalloc(reinterpret_cast<void **>(&d_bytes), std::max<size_t>(n_win * nb, 1)));
     CUX(cudaMalloc(reinterpret_cast<void **>(&d_iters), std::max<size_t>(n_win, 1)));
     CUX(cudaMemcpyAsync(d_sym, sym, n_win * N * 8, cudaMemcpyHostToDevice, c->stream));
     CUX(cudaMemsetAsync(dL, 0, std::max<size_t>(n_win * N * 4, 4), c->stream));
     CUX(cudaMemsetAsync(dE, 0, std::max<size_t>(n_win * E * 4, 4), c->stream));
     CUX(cudaMemsetAsync(dM, 0, std::max<size_t>(n_win * E * 4, 4), c->stream));
+    CUX(cudaMemsetAsync(dS, 0, std::max<size_t>(n_win * E * 4, 4), c->stream));
     DecodeParams p = {};
     p.sym = reinterpret_cast<const float2 *>(d_sym);
     p.n_sym = (long long)(n_win * N);
     p.n_win = (long long)n_win;
     p.max_iters = max_iters; p.early_stop = early_stop ? 1 : 0; p.thr = c->t.M / 8;
     p.out_bytes = d_bytes; p.out_iters = d_iters;
-    p.dbgL = dL; p.dbgE = dE; p.dbgM = dM;
+    p.dbgL = dL; p.dbgE = dE; p.dbgM = dM; p.dbgS = dS;
     st = launch_decode(c, fam, LDPC535_METHOD_SUMPRODUCT, true, p, c->stream);
     if (st) { cleanup(); return st; }
     if (out_L) CUX(cudaMemcpyAsync(out_L, dL, n_win * N * 4, cudaMemcpyDeviceToHost, c->stream));
