@@ -7,12 +7,14 @@
  * tests; a GNU Radio build does not need this file.
  */
 #include <ldpc_ece535a/ldpc_decoder_cb.h>
+#include <ldpc_ece535a/image_sink.h>
 #include <ldpc_ece535a/ldpc_encoder_bc.h>
 
 #include <cstring>
 #include <exception>
 #include <string>
 
+#include "image_sink_impl.h"
 #include "ldpc_decoder_cb_impl.h"
 #include "sync_replay.h"
 
@@ -70,6 +72,24 @@ HARNESS_API void *ldpc535_blk_encoder_new(void)
         g_err = e.what();
         return nullptr;
     }
+}
+
+HARNESS_API void *ldpc535_blk_image_sink_new(void)
+{
+    try {
+        blk *h = new blk();
+        h->b = image_sink::make();
+        return h;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+HARNESS_API unsigned ldpc535_blk_image_sink_files(void *p)
+{
+    image_sink_impl *s = dynamic_cast<image_sink_impl *>(static_cast<blk *>(p)->b.get());
+    return s ? s->files_written() : 0;
 }
 
 HARNESS_API void ldpc535_blk_free(void *p) { delete static_cast<blk *>(p); }

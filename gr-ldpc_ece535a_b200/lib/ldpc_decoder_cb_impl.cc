@@ -21,12 +21,23 @@
 
 #include <algorithm>
 #include <cstdlib>
-#include <iostream>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 
 namespace gr {
 namespace ldpc_ece535a {
+
+namespace {
+// console lines the reference prints with std::cout; C stdio keeps the module independent of
+// which libstdc++ the host process (e.g. Python) happens to have loaded
+void say(const char *line)
+{
+    std::fputs(line, stdout);
+    std::fputc('\n', stdout);
+    std::fflush(stdout);
+}
+}  // namespace
 
 namespace {
 int device_from_env()
@@ -61,10 +72,10 @@ ldpc_decoder_cb_impl::ldpc_decoder_cb_impl(const int method)
     d_threshold = d_M / 8;
 
     // same console line as the reference constructor (:108-116)
-    if (d_method == 3) std::cout << "Decoding method: Hard Decision" << std::endl;
-    else if (d_method == 2) std::cout << "Decoding method: Bit Flipping" << std::endl;
-    else if (d_method == 1) std::cout << "Decoding method: Sum Product" << std::endl;
-    else std::cout << "Decoding method: Log Domain Simple" << std::endl;
+    if (d_method == 3) say("Decoding method: Hard Decision");
+    else if (d_method == 2) say("Decoding method: Bit Flipping");
+    else if (d_method == 1) say("Decoding method: Sum Product");
+    else say("Decoding method: Log Domain Simple");
 
     // One output byte needs 16 input symbols; whole frames only.  Hints for the scheduler's
     // buffer sizing, they do not change what is produced.
@@ -159,13 +170,12 @@ int ldpc_decoder_cb_impl::general_work(int noutput_items, gr_vector_int &ninput_
         produced = d_sync.run(*this, d_ninput, noutput_items, d_N, d_nbytes, d_threshold, out,
                               &consumed, [this](int ev) {
                                   d_events.push_back(ev);
-                                  if (ev == EV_IN_SYNC) std::cout << "IN SYNC" << std::endl;
-                                  else if (ev == EV_IN_SYNC_INVERTED)
-                                      std::cout << "IN SYNC; PHASE INVERTED" << std::endl;
-                                  else std::cout << "MAX ERRORS; OUT OF SYNC" << std::endl;
+                                  if (ev == EV_IN_SYNC) say("IN SYNC");
+                                  else if (ev == EV_IN_SYNC_INVERTED) say("IN SYNC; PHASE INVERTED");
+                                  else say("MAX ERRORS; OUT OF SYNC");
                               });
     } catch (const std::exception &e) {
-        std::cerr << e.what() << std::endl;         // no CPU fallback: stop the flowgraph
+        std::fprintf(stderr, "%s\n", e.what());     // no CPU fallback: stop the flowgraph
         return WORK_DONE;
     }
     d_in = NULL;

@@ -18,7 +18,7 @@
 
 #include <algorithm>
 #include <cstdlib>
-#include <iostream>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 
@@ -67,8 +67,8 @@ int ldpc_encoder_bc_impl::general_work(int noutput_items, gr_vector_int &ninput_
     if (frames > 0) {
         const int st = ldpc535_encode_batch(d_code, in, (size_t)frames, reinterpret_cast<float *>(out));
         if (st != LDPC535_OK) {
-            std::cerr << "ldpc_encoder_bc: GPU encode failed: " << ldpc535_strerror(st) << " ("
-                      << ldpc535_last_error() << ")" << std::endl;
+            std::fprintf(stderr, "ldpc_encoder_bc: GPU encode failed: %s (%s)\n", ldpc535_strerror(st),
+                         ldpc535_last_error());
             return WORK_DONE;                       // no CPU fallback
         }
     }

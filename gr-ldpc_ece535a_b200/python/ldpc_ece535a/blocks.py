@@ -32,6 +32,9 @@ def blocks_lib():
         h.ldpc535_blk_decoder_new.restype = vp
         h.ldpc535_blk_decoder_new.argtypes = [i]
         h.ldpc535_blk_encoder_new.restype = vp
+        h.ldpc535_blk_image_sink_new.restype = vp
+        h.ldpc535_blk_image_sink_files.argtypes = [vp]
+        h.ldpc535_blk_image_sink_files.restype = C.c_uint
         h.ldpc535_blk_free.argtypes = [vp]
         h.ldpc535_blk_name.restype = C.c_char_p
         h.ldpc535_blk_name.argtypes = [vp]
@@ -114,6 +117,23 @@ class ldpc_encoder_bc(_Block):
 
     def __init__(self):
         super().__init__(blocks_lib().ldpc535_blk_encoder_new())
+
+
+class image_sink(_Block):
+    """bytes in, nothing out: reassembles BMP files from the decoded stream (host I/O only)."""
+    _in_dtype, _out_dtype = np.uint8, np.uint8
+
+    def __init__(self):
+        super().__init__(blocks_lib().ldpc535_blk_image_sink_new())
+
+    def work(self, items):
+        """One scheduler call of a sync sink: consumes everything it is shown."""
+        items = np.ascontiguousarray(items, np.uint8)
+        _, consumed = self.general_work(items, items.size)
+        return consumed
+
+    def files_written(self):
+        return int(blocks_lib().ldpc535_blk_image_sink_files(self._h))
 
 
 def sync_replay_table(bytes_pos, bytes_neg, synd_pos, synd_neg, ninput, noutput, N, nbytes,

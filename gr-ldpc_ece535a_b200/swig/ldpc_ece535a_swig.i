@@ -13,6 +13,7 @@
 %{
 #include "ldpc_ece535a/ldpc_decoder_cb.h"
 #include "ldpc_ece535a/ldpc_encoder_bc.h"
+#include "ldpc_ece535a/image_sink.h"
 %}
 
 %include "ldpc_ece535a/ldpc_decoder_cb.h"
@@ -20,3 +21,6 @@ GR_SWIG_BLOCK_MAGIC2(ldpc_ece535a, ldpc_decoder_cb);
 
 %include "ldpc_ece535a/ldpc_encoder_bc.h"
 GR_SWIG_BLOCK_MAGIC2(ldpc_ece535a, ldpc_encoder_bc);
+
+%include "ldpc_ece535a/image_sink.h"
+GR_SWIG_BLOCK_MAGIC2(ldpc_ece535a, image_sink);

@@ -254,3 +254,27 @@ def load_ref_codes():
         codes[name] = {"H": H, "source_words": np.array(e.get("source_words", []), np.int32)}
     codes["shipped"] = codes[raw["shipped"]]
     return codes
+
+
+class ImageSinkOracle:
+    """lib/image_sink_impl.cc:46-84 restated: header scan with 19 bytes of look-ahead inside
+    one work() call, file written (announced size only) when the NEXT header arrives."""
+    DIB = (12, 40, 52, 56, 64, 108, 124)
+
+    def __init__(self):
+        self.buffer = bytearray()
+        self.file_size = 0
+        self.files = []            # every file the block would have written to result.bmp
+
+    def work(self, data):
+        d = bytes(bytearray(data))
+        n = len(d)
+        for i in range(n):
+            if (i < n - 18 and d[i] == 0x42 and d[i + 1] == 0x4D and d[i + 6] == 0 and d[i + 7] == 0
+                    and d[i + 8] == 0 and d[i + 9] == 0 and d[i + 14] in self.DIB):
+                if self.file_size > 0 and len(self.buffer) >= self.file_size:
+                    self.files.append(bytes(self.buffer[:self.file_size]))
+                self.buffer = bytearray()
+                self.file_size = (d[i + 5] << 24) | (d[i + 4] << 16) | (d[i + 3] << 8) | d[i + 2]
+            self.buffer.append(d[i])
+        return n
