@@ -55,6 +55,101 @@ void for_each_set(const uint64_t *r, int lo, int hi, Fn fn)
     }
 }
 
+// Storage column of every check in the CTA-per-codeword kernel's message array
+// (index = slot * M + column, bank = column mod 32).  The check phase walks columns in order
+// and is conflict-free for any placement; in the variable phase lane l of a warp handles bit
+// 32 w + l and touches, for its k-th check, the bank of THAT check's column -- with the checks
+// in file order a random code gives ~3.4 wavefronts per access.  Greedy placement: take the
+// checks one by one and give each the bank (with room left) where its edges collide least with
+// the edges already placed in the same (bit-warp, k) access group; then a few passes move
+// still-colliding checks to a better bank by swapping.  Relabels storage only: the arithmetic
+// (edge order inside a bit's sums, slot order inside a check) is untouched.
+void place_checks_for_banks(CodeTables &t)
+{
+    const int M = t.M, rows = M / 32, dv = std::max(t.dv_max, 1);
+    const int n_groups = ((t.N + 31) / 32) * dv;
+    // group of every CSR edge: (warp of its bit, rank of its check among the bit's checks)
+    std::vector<int32_t> grp(t.E);
+    for (int c = 0; c < t.N; c++)
+        for (int q = t.col_ptr[c], k = 0; q < t.col_ptr[c + 1]; q++, k++)
+            grp[t.edge_of_col[q]] = (c / 32) * dv + k;
+    std::vector<uint16_t> cnt((size_t)n_groups * 32, 0);
+    std::vector<int> bank(M, -1), fill(32, 0);
+    auto cost = [&](int j, int b) {
+        int c = 0;
+        for (int e = t.row_ptr[j]; e < t.row_ptr[j + 1]; e++) c += cnt[(size_t)grp[e] * 32 + b];
+        return c;
+    };
+    auto add = [&](int j, int b, int d) {
+        for (int e = t.row_ptr[j]; e < t.row_ptr[j + 1]; e++) cnt[(size_t)grp[e] * 32 + b] += d;
+    };
+    for (int j = 0; j < M; j++) {
+        int best = -1, best_cost = 1 << 30;
+        for (int o = 0; o < 32; o++) {
+            const int b = (j + o) & 31;                 // rotate the tie-break so banks fill evenly
+            if (fill[b] >= rows) continue;
+            const int c = cost(j, b);
+            if (c < best_cost || (c == best_cost && fill[b] < fill[best])) { best = b; best_cost = c; }
+        }
+        bank[j] = best;
+        fill[best]++;
+        add(j, best, +1);
+    }
+    // improvement: swap a colliding check with a check of another bank when that lowers the total
+    std::vector<std::vector<int>> members(32);
+    for (int j = 0; j < M; j++) members[bank[j]].push_back(j);
+    for (int pass = 0; pass < 40; pass++) {
+        int moved = 0;
+        for (int j = 0; j < M; j++) {
+            const int b0 = bank[j];
+            add(j, b0, -1);
+            const int c0 = cost(j, b0);
+            if (c0 == 0) { add(j, b0, +1); continue; }
+            int best_b = -1, best_q = -1, best_gain = 0;
+            for (int b = 0; b < 32; b++) {
+                if (b == b0) continue;
+                const int cj = cost(j, b);
+                if (cj >= c0) continue;
+                // partner from bank b that can move to b0 cheaply (sample a few)
+                const auto &mb = members[b];
+                for (size_t z = 0; z < mb.size() && z < 16; z++) {
+                    const int q = mb[(j + pass * 13 + z * 7) % mb.size()];
+                    add(q, b, -1);
+                    const int gain = (c0 + cost(q, b)) - (cost(j, b) + cost(q, b0));
+                    add(q, b, +1);
+                    if (gain > best_gain) { best_gain = gain; best_b = b; best_q = q; }
+                }
+            }
+            if (best_b >= 0) {
+                add(best_q, best_b, -1);
+                add(best_q, b0, +1);
+                add(j, best_b, +1);
+                bank[j] = best_b;
+                bank[best_q] = b0;
+                auto &ma = members[b0];
+                auto &mb = members[best_b];
+                *std::find(ma.begin(), ma.end(), j) = best_q;
+                *std::find(mb.begin(), mb.end(), best_q) = j;
+                moved++;
+            } else {
+                add(j, b0, +1);
+            }
+        }
+        if (!moved) break;
+    }
+    std::vector<int> next(32, 0);
+    for (int j = 0; j < M; j++) t.chk_pos[j] = bank[j] + 32 * next[bank[j]]++;
+    // residual: access groups' wavefronts beyond one (0 = conflict-free variable phase)
+    long long extra = 0;
+    for (size_t g = 0; g < (size_t)n_groups; g++) {
+        int mx = 0;
+        for (int b = 0; b < 32; b++) mx = std::max<int>(mx, cnt[g * 32 + b]);
+        extra += std::max(0, mx - 1);
+    }
+    t.bank_extra_wavefronts = (int)extra;
+    t.bank_groups = n_groups;
+}
+
 }  // namespace
 
 int build_code_tables(const int32_t *row_ptr_in, const int32_t *col_idx_in, int M, int N,
@@ -191,13 +286,18 @@ int build_code_tables(const int32_t *row_ptr_in, const int32_t *col_idx_in, int 
         t.dv_max = std::max(t.dv_max, d);
     }
     t.edge_slot.resize(E);
+    t.chk_pos.resize(M);
+    for (int j = 0; j < M; j++) t.chk_pos[j] = j;
+    if (M >= 64 && M % 32 == 0) place_checks_for_banks(t);
+    t.chk_deg_slot.assign(M, 0);
+    for (int j = 0; j < M; j++) t.chk_deg_slot[t.chk_pos[j]] = t.chk_deg[j];
     if ((size_t)t.dc_max * M <= 65535) {
         t.chk_var.assign((size_t)t.dc_max * M, 0xFFFF);
         t.var_slot.assign((size_t)t.dv_max * N, 0xFFFF);
         for (int j = 0; j < M; j++)
             for (int e = t.row_ptr[j], s = 0; e < t.row_ptr[j + 1]; e++, s++) {
-                t.chk_var[(size_t)s * M + j] = (uint16_t)t.col_idx[e];
-                t.edge_slot[e] = s * M + j;
+                t.chk_var[(size_t)s * M + t.chk_pos[j]] = (uint16_t)t.col_idx[e];
+                t.edge_slot[e] = s * M + t.chk_pos[j];
             }
         for (int c = 0; c < N; c++)
             for (int q = t.col_ptr[c], k = 0; q < t.col_ptr[c + 1]; q++, k++)

@@ -31,6 +31,12 @@ struct CodeTables {
     std::vector<uint16_t> chk_var;      // [dc_max][M]  variable of (slot, check) or 0xFFFF
     std::vector<uint16_t> var_slot;     // [dv_max][N]  message index of the k-th check of a
                                         //              variable (checks ascending) or 0xFFFF
+    std::vector<int32_t> chk_pos;       // [M]  storage column of check j in the message array (a
+                                        //      permutation chosen to avoid shared-memory bank
+                                        //      conflicts in the variable phase; identity for M < 64)
+    std::vector<uint8_t> chk_deg_slot;  // [M]  degree of the check stored in column c
+    int bank_extra_wavefronts = 0;      // variable-phase access groups' wavefronts beyond one
+    int bank_groups = 0;
     std::vector<uint8_t> chk_deg;       // [M]
     std::vector<uint8_t> var_deg;       // [N]
     std::vector<int32_t> edge_slot;     // [E]  CSR edge id -> message index (message dumps)

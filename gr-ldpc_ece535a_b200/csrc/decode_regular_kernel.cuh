@@ -1,0 +1,162 @@
+// CTA-per-codeword sum-product kernel for REGULAR codes (every check of degree DC, every bit of
+// degree DV; BASELINE config 4's (3,6)-regular n = 8192 code): the generic decode_block_kernel
+// with everything a regular code does not need removed -- no degree table, no padded-slot
+// predicates -- plus
+//   * the bit's DV message addresses packed into one 8-byte table row (one LDS.64 per bit
+//     instead of DV 16-bit loads); that table is staged into shared memory once per CTA by a
+//     1-D TMA bulk copy and amortised over all the codewords the CTA decodes;
+//   * early stop from hard-decision tags carried in bit 30 of the stored messages (see
+//     decode_block_kernel): the parity of a check falls out of the sign-XOR the check update
+//     computes anyway, so there is no syndrome pass and only two barriers per iteration.
+// Arithmetic and operation order are spa_math.cuh's: results equal the generic kernels' bit for
+// bit.  Shared memory: msg[DC*M] | r[N] | hard[N/32] | red | var table [N][4] u16.
+#pragma once
+#include "decode_kernels.cuh"
+
+namespace ldpc535 {
+
+__host__ __device__ inline size_t regular_smem_bytes(int dc, int M, int N)
+{
+    size_t b = 16 + 4 * (size_t)dc * M + 4 * (size_t)N + 4 * (size_t)((N + 31) >> 5) + 16;
+    b = (b + 15) & ~(size_t)15;
+    return b + 8 * (size_t)N;
+}
+
+template <int DC, int DV>
+__global__ void __launch_bounds__(1024, 1)
+decode_regular_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row4)
+{
+    static_assert(DV <= 4, "the packed bit table holds four addresses");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int M = p.M, N = p.N;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int nwords = (N + 31) >> 5;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float *msg = reinterpret_cast<float *>(smem_raw + 16);
+    float *r = msg + (size_t)DC * M;
+    uint32_t *hard = reinterpret_cast<uint32_t *>(r + N);
+    int *red = reinterpret_cast<int *>(hard + nwords);
+    const size_t tab_off = ((size_t)16 + 4 * (size_t)DC * M + 4 * (size_t)N + 4 * (size_t)nwords + 16 + 15) & ~(size_t)15;
+    const uint2 *vt = reinterpret_cast<const uint2 *>(smem_raw + tab_off);
+
+    // stage the packed bit table (8 N bytes) once per CTA: TMA bulk copy, mbarrier completion
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = 8u * (uint32_t)N;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+        tma_bulk_g2s(smem_raw + tab_off, var_row4, bytes, bar);
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+        }
+    }
+
+    const bool tag = p.early_stop != 0;
+    for (long long w = blockIdx.x; w < p.n_win; w += gridDim.x) {
+        const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
+        const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
+        const bool ok = off >= 0 && off + N <= p.n_sym;
+        __syncthreads();                                   // previous window fully drained
+        for (int i = tid; i < N; i += nt) r[i] = ok ? (-pol * kSpaScale) * load_re(p, off + i) : 0.f;
+        if (tid == 0) red[0] = 0;
+        __syncthreads();
+        // M_ji = r_i on every edge, stored as t = copysign(2^-|M|, M), no tags yet
+        for (int i = tid; i < N; i += nt) {
+            const uint2 a = vt[i];
+            const float t = to_check_msg(r[i]);
+            msg[a.x & 0xffffu] = t;
+            if (DV > 1) msg[a.x >> 16] = t;
+            if (DV > 2) msg[a.y & 0xffffu] = t;
+            if (DV > 3) msg[a.y >> 16] = t;
+        }
+        __syncthreads();
+
+        int iters = p.max_iters;
+        bool clean = false;
+        for (int h = 0; h < p.max_iters; h++) {
+            // ---- check nodes (+ parity of the previous iteration's decisions from the tags) ----
+            uint32_t tagbad = 0;
+            for (int j = tid; j < M; j += nt) {
+                float m[DC];
+#pragma unroll
+                for (int s = 0; s < DC; s++) m[s] = msg[s * M + j];
+                tagbad |= check_node_spa<DC, true>(m);
+#pragma unroll
+                for (int s = 0; s < DC; s++) msg[s * M + j] = m[s];
+            }
+            if (tag) {
+                const int bad = __syncthreads_or((int)(tagbad & 0x40000000u));
+                if (h > 0 && !bad) { iters = h; clean = true; break; }
+            } else {
+                __syncthreads();
+            }
+            // ---- variable nodes: L, hard decision, next messages (tagged with the decision) ----
+            for (int base = 0; base < N; base += nt) {
+                const int i = base + tid;
+                bool b = false;
+                if (i < N) {
+                    const uint2 a = vt[i];
+                    int idx[4] = {(int)(a.x & 0xffffu), (int)(a.x >> 16), (int)(a.y & 0xffffu), (int)(a.y >> 16)};
+                    float x[DV];
+#pragma unroll
+                    for (int k = 0; k < DV; k++) x[k] = msg[idx[k]];
+                    const float L = var_node_spa<DV>(x, DV, r[i]);
+                    b = (L <= 0.f);
+                    const uint32_t tagbit = (tag && b) ? 0x40000000u : 0u;
+#pragma unroll
+                    for (int k = 0; k < DV; k++)
+                        msg[idx[k]] = __uint_as_float(__float_as_uint(to_check_msg(x[k])) | tagbit);
+                }
+                const uint32_t wd = __ballot_sync(0xffffffffu, b);
+                if (lane == 0 && i < N) hard[i >> 5] = wd;
+            }
+            __syncthreads();
+        }
+
+        // ---- saturating syndrome weight of the final decision (checkFrame, :236-253) ----
+        int cnt = 0;
+        if (!clean) {
+            for (int j = tid; j < M; j += nt) {
+                uint32_t pj = 0;
+#pragma unroll
+                for (int s = 0; s < DC; s++) {
+                    const int v = __ldg(p.chk_var + s * M + j);
+                    pj ^= hard[v >> 5] >> (v & 31);
+                }
+                cnt += (int)(pj & 1u);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0 && cnt) atomicAdd(&red[0], cnt);
+            __syncthreads();
+            cnt = red[0];
+        }
+        // ---- outputs: data bits M .. N-1, MSB first (:207-219) ----
+        for (int b = tid; b < p.nbytes; b += nt) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int v = M + 8 * b + q;
+                if (v < N) bits |= ((hard[v >> 5] >> (v & 31)) & 1u) << q;
+            }
+            p.out_bytes[w * p.nbytes + b] = ok ? pack_msb_first(bits) : (uint8_t)0;
+        }
+        if (tid == 0) {
+            if (p.out_synd) p.out_synd[w] = ok ? (uint8_t)min(cnt, p.thr + 1) : (uint8_t)255;
+            if (p.out_iters) p.out_iters[w] = ok ? (uint8_t)min(iters, 255) : (uint8_t)255;
+        }
+    }
+}
+
+}  // namespace ldpc535

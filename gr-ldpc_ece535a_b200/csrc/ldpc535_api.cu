@@ -17,6 +17,7 @@
 #include "code_tables.h"
 #include "decode_kernels.cuh"
 #include "decode_c4_kernel.cuh"
+#include "decode_regular_kernel.cuh"
 #include "encode_kernels.cuh"
 #include "host_pack.h"
 #include "ldpc535_default_code.h"
@@ -40,7 +41,7 @@ int fail(int status, const std::string &msg)
             return fail(LDPC535_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3 };
+enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4 };
 
 constexpr int kSlots = 3;                       // pipeline depth of the host-buffer API
 constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot
@@ -67,6 +68,8 @@ struct ldpc535_code {
     uint16_t *d_chk_var = nullptr, *d_var_slot = nullptr;
     uint8_t *d_chk_deg = nullptr;
     int32_t *d_slot_edge = nullptr;
+    uint16_t *d_var_row4 = nullptr;   // [N][4] message addresses of a bit (regular codes, dv <= 4)
+    bool fits_regular = false;
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
     int tabA_bytes = 0, tabB_bytes = 0;
     int dc_t = 0, dv_t = 0;           // template sizes used (6/3 or 16/8), 0 = unsupported degrees
@@ -149,7 +152,7 @@ int finish_create(ldpc535_code *c)
     int st;
     if ((st = upload(&c->d_chk_var, t.chk_var.data(), t.chk_var.size() * 2, c->tabA_bytes))) return st;
     if ((st = upload(&c->d_var_slot, t.var_slot.data(), t.var_slot.size() * 2, c->tabB_bytes))) return st;
-    if ((st = upload(&c->d_chk_deg, t.chk_deg.data(), t.chk_deg.size(), t.chk_deg.size()))) return st;
+    if ((st = upload(&c->d_chk_deg, t.chk_deg_slot.data(), t.chk_deg_slot.size(), t.chk_deg_slot.size()))) return st;
     {
         std::vector<int32_t> slot_edge((size_t)c->dc_t * t.M, -1);
         for (int e = 0; e < t.E; e++) slot_edge[t.edge_slot[e]] = e;
@@ -164,6 +167,20 @@ int finish_create(ldpc535_code *c)
         if ((st = upload(&c->d_Pw, Pw.data(), Pw.size() * 4, Pw.size() * 4))) return st;
     }
 
+    // regular code -> the specialised CTA-per-codeword kernel
+    {
+        bool regular = t.dv_max <= 4;
+        for (int j = 0; j < t.M && regular; j++) regular = t.chk_deg[j] == t.dc_max;
+        for (int v = 0; v < t.N && regular; v++) regular = t.var_deg[v] == t.dv_max;
+        regular = regular && t.dc_max == 6 && t.dv_max == 3 && t.M > 32;
+        if (regular && regular_smem_bytes(6, t.M, t.N) <= c->smem_optin) {
+            std::vector<uint16_t> row4((size_t)t.N * 4, 0);
+            for (int v = 0; v < t.N; v++)
+                for (int k = 0; k < t.dv_max; k++) row4[(size_t)v * 4 + k] = t.var_slot[(size_t)k * t.N + v];
+            if ((st = upload(&c->d_var_row4, row4.data(), row4.size() * 2, row4.size() * 2))) return st;
+            c->fits_regular = true;
+        }
+    }
     c->fits_warp = (t.M <= 32 && t.N <= 64);
     c->is_c4 = tables_match_c4(t);
     const size_t fixed = block_smem_fixed_bytes(c->dc_t, t.M, t.N);
@@ -194,7 +211,7 @@ void release(ldpc535_code *c)
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
-    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_var_row4);
     delete c;
 }
 
@@ -204,6 +221,7 @@ int family_from_name(const char *name, int *out)
     if (!strcmp(name, "warp")) { *out = kWarp; return 0; }
     if (!strcmp(name, "block")) { *out = kBlock; return 0; }
     if (!strcmp(name, "c4-thread")) { *out = kC4Thread; return 0; }
+    if (!strcmp(name, "regular")) { *out = kRegular; return 0; }
     return 1;
 }
 
@@ -212,10 +230,12 @@ int resolve_family(const ldpc535_code *c, int forced, int method)
     int f = forced;
     if (f == kAuto) {
         if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT) f = kC4Thread;
+        else if (c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT) f = kRegular;
         else if (c->fits_warp) f = kWarp;
         else f = kBlock;
     }
     if (f == kC4Thread && !(c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
+    if (f == kRegular && !(c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
     if (f == kWarp && !c->fits_warp) return -1;
     if (f == kBlock && !c->fits_block) return -1;
     return f;
@@ -283,7 +303,7 @@ cudaError_t launch_generic(const ldpc535_code *c, int family, int method, bool d
 int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParams p, cudaStream_t st)
 {
     method = norm_method(method);
-    const int family = resolve_family(c, forced, method);
+    int family = resolve_family(c, forced, method);
     if (family < 0) return fail(LDPC535_ERR_UNSUPPORTED, "kernel family not available for this code/method");
     if (p.n_win == 0) return LDPC535_OK;
     p.M = c->t.M; p.N = c->t.N; p.K = c->t.K; p.E = c->t.E;
@@ -292,7 +312,17 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
     p.slot_edge = c->d_slot_edge;
     p.stage_tables = c->stage_tables; p.tabA_bytes = c->tabA_bytes; p.tabB_bytes = c->tabB_bytes;
     cudaError_t e;
-    if (family == kC4Thread) e = launch_c4_thread(p, dbg, c->sm_count, st);
+    if (family == kRegular && dbg) family = kBlock;            // message dumps live in the generic kernel
+    if (family == kRegular) {
+        auto kern = decode_regular_kernel<6, 3>;
+        const size_t smem = regular_smem_bytes(6, c->t.M, c->t.N);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            const int grid = (int)std::min<long long>(p.n_win, (long long)c->sm_count);
+            kern<<<grid, c->block_threads, smem, st>>>(p, c->d_var_row4);
+            e = cudaGetLastError();
+        }
+    } else if (family == kC4Thread) e = launch_c4_thread(p, dbg, c->sm_count, st);
     else if (c->dc_t == 6) e = launch_generic<6, 3>(c, family, method, dbg, p, st);
     else e = launch_generic<16, 8>(c, family, method, dbg, p, st);
     if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("decode launch: ") + cudaGetErrorString(e));
@@ -387,6 +417,10 @@ int create_common(const int32_t *row_ptr, const int32_t *col_idx, int M, int N, 
         return fail(st, st == LDPC535_ERR_SINGULAR ? "reorderHMatrix: a row has no pivot (singular L/U)"
                                                    : "invalid parity-check matrix");
     }
+    if (getenv("LDPC535_VERBOSE"))
+        fprintf(stderr, "ldpc535: code %dx%d E=%d dc<=%d dv<=%d; message-array placement leaves %d extra "
+                        "shared-memory wavefronts over %d variable-phase access groups\n",
+                c->t.M, c->t.N, c->t.E, c->t.dc_max, c->t.dv_max, c->t.bank_extra_wavefronts, c->t.bank_groups);
     if (device == LDPC535_DEVICE_NONE) {     // tables only: introspection works, compute refuses
         *out = c;
         return LDPC535_OK;
@@ -519,6 +553,7 @@ const char *ldpc535_code_kernel_name(const ldpc535_code *c, int method)
     case kWarp: return "warp";
     case kBlock: return "block";
     case kC4Thread: return "c4-thread";
+    case kRegular: return "regular";
     default: return "unsupported";
     }
 }
@@ -531,6 +566,7 @@ int ldpc535_code_set_kernel(ldpc535_code *c, const char *kernel)
     if (f == kWarp && !c->fits_warp) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the warp kernel");
     if (f == kBlock && !c->fits_block) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the block kernel");
     if (f == kC4Thread && !c->is_c4) return fail(LDPC535_ERR_UNSUPPORTED, "not the shipped 32x64 code");
+    if (f == kRegular && !c->fits_regular) return fail(LDPC535_ERR_UNSUPPORTED, "not a (3,6)-regular code that fits shared memory");
     c->forced = f;
     return LDPC535_OK;
 }

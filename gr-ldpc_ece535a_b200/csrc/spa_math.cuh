@@ -59,15 +59,18 @@ __device__ __forceinline__ float to_check_msg(float M)
 }
 
 // In: m[s] = stored bit->check messages t of one check (padded slots +0).  Out: m[s] = E.
-template <int DC>
-__device__ __forceinline__ void check_node_spa(float (&m)[DC])
+// Returns the XOR of the input bit patterns.  TAGGED: bit 30 of every input carries the hard
+// decision of its bit (|t| <= 1 leaves that bit free); it is masked off here, and bit 30 of the
+// returned word is the parity of the check -- the syndrome test costs one AND per edge.
+template <int DC, bool TAGGED = false>
+__device__ __forceinline__ uint32_t check_node_spa(float (&m)[DC])
 {
     float e[DC];
     uint32_t sx = 0;
 #pragma unroll
     for (int s = 0; s < DC; s++) {
         sx ^= __float_as_uint(m[s]);
-        e[s] = fabsf(m[s]);
+        e[s] = TAGGED ? __uint_as_float(__float_as_uint(m[s]) & 0x3fffffffu) : fabsf(m[s]);
     }
     // prefix (pe, po)[s] = expansion over slots < s ; suffix (se, so)[s] over slots > s.
     // The first step of each recurrence and the two end combinations below are written out
@@ -102,6 +105,7 @@ __device__ __forceinline__ void check_node_spa(float (&m)[DC])
         // mag >= 0 (even >= odd): attach sign(all inputs) ^ sign(own input)
         m[s] = __uint_as_float(__float_as_uint(mag) ^ ((__float_as_uint(m[s]) & 0x80000000u) ^ base));
     }
+    return sx;
 }
 
 // Min-sum check update (decodeLogDomainSimple, lib/ldpc_decoder_cb_impl.cc:349-376):

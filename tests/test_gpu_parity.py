@@ -367,9 +367,12 @@ def test_c8k_encode_satisfies_every_check(c8k):
     assert np.array_equal(c, bits[0][:c8k.M])
 
 
-def test_c8k_decode_vs_sparse_oracle(c8k):
+@pytest.mark.parametrize("kernel", ["regular", "block"])
+def test_c8k_decode_vs_sparse_oracle(c8k, kernel):
     """Config 4's code: decisions and iteration counts vs the sparse restatement (checked
     bit-identical to the dense one on the shipped code by the CPU suite)."""
+    with_kernel(c8k, kernel)
+    assert c8k.kernel_name() == kernel
     rng = np.random.default_rng(13)
     n = 12
     data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
@@ -386,6 +389,35 @@ def test_c8k_decode_vs_sparse_oracle(c8k):
             assert np.array_equal(np.packbits(vhat[c8k.M:].astype(np.uint8)), b[f]), (ebn0, f)
     b, sy, it = c8k.decode(clean, method=1)
     assert np.array_equal(b, data) and not sy.any() and (it == 1).all()
+    # fixed iterations (no early stop) and a short limit that most frames do not reach
+    sigma = np.float32(np.sqrt(10.0 ** (-2.0 / 10.0)))
+    noisy = clean.copy()
+    noisy.real += rng.standard_normal(clean.shape, dtype=np.float32) * sigma
+    for iters, early in ((6, False), (9, True)):
+        b, sy, it = c8k.decode(noisy, method=1, max_iters=iters, early_stop=early)
+        for f in range(4):
+            vhat, run = O.decode_spa_sparse(noisy[f].real, tables, c8k.M, c8k.N, iters, early)
+            assert it[f] == run
+            assert np.array_equal(np.packbits(vhat[c8k.M:].astype(np.uint8)), b[f])
+    c8k.set_kernel(None)
+
+
+def test_c8k_kernels_agree(c8k):
+    """regular vs generic CTA kernel on the same noisy frames: identical bytes, syndrome weights
+    (saturating) and iteration counts."""
+    rng = np.random.default_rng(16)
+    n = 300
+    data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
+    noisy = c8k.encode(data)
+    noisy.real += rng.standard_normal(noisy.shape, dtype=np.float32) * np.float32(0.8)
+    res = {}
+    for kern in ("regular", "block"):
+        c8k.set_kernel(kern)
+        res[kern] = [c8k.decode(noisy, method=1, max_iters=mi, early_stop=es) for mi, es in ((50, True), (8, True), (5, False))]
+    c8k.set_kernel(None)
+    for a, b in zip(res["regular"], res["block"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
 
 
 def test_c8k_messages_within_tolerance(c8k):
