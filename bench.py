@@ -44,7 +44,11 @@ MAX_ITERS = 50
 K_INFO, N_SYM, M_CHK, E_EDGES = 32, 64, 32, 168
 BYTES_PER_CW = 8 * N_SYM + K_INFO // 8 + 2          # complex64 in + packed out + 2
 XU_PER_EDGE_ITER = 4                                # SURVEY 8d algorithmic figure (tanh, log, div)
+MUFU_PER_EDGE_ITER = 3                              # what the kernels execute: 1 ex2 + 2 lg2 (spa_math.cuh)
 SM_COUNT, XU_LANES = 148, 16
+# XU-pipe ceiling measured on this pool's B200 with tools/microbench/mufu_peak.cu (independent
+# ex2/lg2 streams, 1 ex2 : 2 lg2 mix): 15.9 MUFU lanes/clk/SM at 1965 MHz (profiles/r1_microbench.txt)
+XU_MEASURED_PEAK = 4.63e12
 
 
 def config(n_cw, n_gpus):
@@ -328,12 +332,15 @@ def run_gpu(args):
             "kernel": code.kernel_name(L.METHOD_SUMPRODUCT), "kernel_ms": kern_ms,
             "note": "a fixed-50-iteration sum-product is bound by the SM special-function/issue "
                     "pipes, not HBM (SURVEY 8d); `governing` is the roofline that applies",
-            "governing": {"bound": "sm_xu", "achieved": XU_PER_EDGE_ITER * edge_it / 1e12,
-                          "peak": xu_peak_ops / 1e12, "unit": "T XU-op/s",
-                          "frac": XU_PER_EDGE_ITER * edge_it / xu_peak_ops,
+            "governing": {"bound": "sm_xu", "achieved": MUFU_PER_EDGE_ITER * edge_it / 1e12,
+                          "peak": XU_MEASURED_PEAK / 1e12, "unit": "T MUFU/s",
+                          "frac": MUFU_PER_EDGE_ITER * edge_it / XU_MEASURED_PEAK,
                           "edge_iterations_per_s": edge_it,
-                          "def": "4 XU ops per edge-iteration (tanh, log, div: SURVEY 8d) x E=168 x 50 "
-                                 "iterations per codeword; peak = 148 SMs x 16 XU lanes x max SM clock"}}
+                          "frac_algorithmic_4xu_nominal": XU_PER_EDGE_ITER * edge_it / xu_peak_ops,
+                          "def": "executed MUFU (3 per edge-iteration: 1 ex2 + 2 lg2) x E=168 x 50 iterations per "
+                                 "codeword against the XU-pipe peak measured with tools/microbench/mufu_peak.cu; "
+                                 "frac_algorithmic_4xu_nominal uses SURVEY 8d's 4 XU ops per edge-iteration "
+                                 "against 148 SMs x 16 lanes x max SM clock"}}
         line = {"metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

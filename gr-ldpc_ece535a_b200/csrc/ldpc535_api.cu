@@ -190,6 +190,7 @@ int finish_create(ldpc535_code *c)
     int nt = std::max(t.M, (t.N + 1) / 2);
     nt = std::min(1024, ((nt + 31) / 32) * 32);
     c->block_threads = std::max(nt, 64);
+    if (const char *e = getenv("LDPC535_BLOCK_THREADS")) c->block_threads = std::max(64, std::min(1024, atoi(e) / 32 * 32));
     if (!c->fits_warp && !c->fits_block)
         return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the shared-memory resident decoder");
     return LDPC535_OK;
