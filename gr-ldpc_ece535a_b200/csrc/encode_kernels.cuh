@@ -81,9 +81,20 @@ encode_small_kernel(const EncodeParams p)
 }
 
 // ---- generic: a CTA encodes a tile of kEncTile frames.  Data words sit in shared memory
-// (broadcast reads); thread j owns parity row j and streams its bit-packed row of P once
-// per tile (word-major layout -> coalesced), accumulating acc_t ^= P_jw & d_tw.
-constexpr int kEncTile = 16;
+// (broadcast reads); a thread owns kEncRows parity rows and streams their bit-packed rows of P
+// once per tile (word-major layout -> coalesced, served by L2), accumulating
+// acc[t][r] ^= P[row_r][w] & d[t][w] with one LOP3 each.  Every 16-byte broadcast load of data
+// feeds 4 * kEncRows LOP3s, so the integer pipe, not the shared-memory pipe, sets the pace:
+// M*K/32 AND-XOR words per frame (524 288 for the n = 8192 code) at 64 lanes/clk/SM bound this
+// kernel at ~36 % of the HBM write roofline.
+#ifndef ENC_TILE
+#define ENC_TILE 16
+#endif
+#ifndef ENC_ROWS
+#define ENC_ROWS 4
+#endif
+constexpr int kEncTile = ENC_TILE;
+constexpr int kEncRows = ENC_ROWS;
 constexpr int kEncThreads = 256;
 
 __host__ __device__ inline size_t encode_generic_smem_bytes(int kwords, int mwords)
@@ -122,27 +133,37 @@ encode_generic_kernel(const EncodeParams p)
             dsm[idx] = word;
         }
         __syncthreads();
-        for (int jb = 0; jb < M; jb += kEncThreads) {
-            const int j = jb + tid;
-            uint32_t acc[kEncTile];
+        for (int jb = 0; jb < M; jb += kEncThreads * kEncRows) {
+            uint32_t acc[kEncRows][kEncTile];
 #pragma unroll
-            for (int t = 0; t < kEncTile; t++) acc[t] = 0;
-            if (j < M) {
-                for (int w = 0; w < kw4; w += 4) {
-                    uint32_t pw[4];
+            for (int r = 0; r < kEncRows; r++)
 #pragma unroll
-                    for (int q = 0; q < 4; q++) pw[q] = (w + q < p.kwords) ? __ldg(p.Pw + (size_t)(w + q) * M + j) : 0u;
+                for (int t = 0; t < kEncTile; t++) acc[r][t] = 0;
+            for (int w = 0; w < kw4; w += 4) {
+                uint32_t pw[kEncRows][4];
 #pragma unroll
-                    for (int t = 0; t < kEncTile; t++) {
-                        const uint4 dd = *reinterpret_cast<const uint4 *>(dsm + (size_t)t * kw4 + w);
-                        acc[t] ^= (pw[0] & dd.x) ^ (pw[1] & dd.y) ^ (pw[2] & dd.z) ^ (pw[3] & dd.w);
-                    }
+                for (int r = 0; r < kEncRows; r++) {
+                    const int j = jb + r * kEncThreads + tid;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        pw[r][q] = (j < M && w + q < p.kwords) ? __ldg(p.Pw + (size_t)(w + q) * M + j) : 0u;
+                }
+#pragma unroll
+                for (int t = 0; t < kEncTile; t++) {
+                    const uint4 dd = *reinterpret_cast<const uint4 *>(dsm + (size_t)t * kw4 + w);
+#pragma unroll
+                    for (int r = 0; r < kEncRows; r++)
+                        acc[r][t] ^= (pw[r][0] & dd.x) ^ (pw[r][1] & dd.y) ^ (pw[r][2] & dd.z) ^ (pw[r][3] & dd.w);
                 }
             }
 #pragma unroll
-            for (int t = 0; t < kEncTile; t++) {
-                const uint32_t wd = __ballot_sync(0xffffffffu, __popc(acc[t]) & 1);
-                if (lane == 0 && j < M) csm[(size_t)t * p.mwords + (j >> 5)] = wd;
+            for (int r = 0; r < kEncRows; r++) {
+                const int j = jb + r * kEncThreads + tid;
+#pragma unroll
+                for (int t = 0; t < kEncTile; t++) {
+                    const uint32_t wd = __ballot_sync(0xffffffffu, __popc(acc[r][t]) & 1);
+                    if (lane == 0 && j < M) csm[(size_t)t * p.mwords + (j >> 5)] = wd;
+                }
             }
         }
         __syncthreads();

@@ -468,3 +468,52 @@ def test_device_info_is_b200():
     assert L.device_count() >= 1
     info = L.device_info(0)
     assert info["sm"][0] == 10, info
+
+
+# ---------------------------------------------------------------------------------------
+# larger fixed-seed sets and full-size properties
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,ebn0,iters,early", [(100_000, 2.0, 5, 1), (100_000, 4.0, 5, 1), (20_000, 2.0, 50, 0)])
+def test_decoder_large_fixed_seed_set_vs_oracle(c4, shipped, n, ebn0, iters, early):
+    """fp32 kernels against the fp64 oracle on a large seeded set: every hard decision, iteration
+    count and syndrome weight identical (the bar BASELINE.json sets for the fixed-seed test set)."""
+    rng = np.random.default_rng(2024 + iters)
+    data = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    sym = c4.encode(data)
+    sym.real += rng.standard_normal(sym.shape, dtype=np.float32) * np.float32(np.sqrt(10.0 ** (-ebn0 / 10.0)))
+    b, sy, it = c4.decode(sym, method=1, max_iters=iters, early_stop=early)
+    wb, wit, wsy, _ = O.decode_frames(sym, shipped["Hp"], method=1, iterations=iters, early_stop=bool(early),
+                                      threads=os.cpu_count() or 4)
+    bad = np.nonzero((b != wb).any(axis=1) | (it != wit) | (sy != wsy))[0]
+    assert bad.size == 0, "%d of %d frames differ, first %s" % (bad.size, n, bad[:5])
+
+
+def test_config3_full_size_round_trip(c4):
+    """BASELINE config 3's size (10 M codewords), device-resident: encode -> decode returns the
+    data for every frame in one iteration (noiseless), and with the bench's noise every frame
+    runs exactly the fixed 50 iterations."""
+    import torch
+    n = 10_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    d = torch.randint(0, 256, (n, 4), dtype=torch.uint8, device="cuda", generator=g)
+    sym = torch.empty((n, 64, 2), dtype=torch.float32, device="cuda")
+    ob = torch.empty((n, 4), dtype=torch.uint8, device="cuda")
+    os_ = torch.empty(n, dtype=torch.uint8, device="cuda")
+    oi = torch.empty(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    c4.encode_dev(d.data_ptr(), n, sym.data_ptr())
+    c4.decode_dev(sym.data_ptr(), n * 64, n, ob.data_ptr(), os_.data_ptr(), oi.data_ptr())
+    c4.sync()
+    assert bool((ob == d).all()) and int(os_.max()) == 0 and int(oi.min()) == 1 and int(oi.max()) == 1
+    # linearity of the code: the XOR of two codewords is the codeword of the XORed data
+    d2 = torch.randint(0, 256, (n, 4), dtype=torch.uint8, device="cuda", generator=g)
+    sym2 = torch.empty_like(sym)
+    c4.encode_dev(d2.data_ptr(), n, sym2.data_ptr())
+    c4.sync()
+    prod = sym[:, :, 0] * sym2[:, :, 0]                       # +1 where bits equal: BPSK of ~(a ^ b)
+    sym2[:, :, 0] = -prod                                     # BPSK of a ^ b
+    del prod
+    c4.decode_dev(sym2.data_ptr(), n * 64, n, ob.data_ptr(), os_.data_ptr(), oi.data_ptr())
+    c4.sync()
+    assert bool((ob == (d ^ d2)).all()) and int(os_.max()) == 0
