@@ -514,6 +514,7 @@ def test_config3_full_size_round_trip(c4):
     prod = sym[:, :, 0] * sym2[:, :, 0]                       # +1 where bits equal: BPSK of ~(a ^ b)
     sym2[:, :, 0] = -prod                                     # BPSK of a ^ b
     del prod
+    torch.cuda.synchronize()                                  # torch's stream -> the handle's stream
     c4.decode_dev(sym2.data_ptr(), n * 64, n, ob.data_ptr(), os_.data_ptr(), oi.data_ptr())
     c4.sync()
     assert bool((ob == (d ^ d2)).all()) and int(os_.max()) == 0
