@@ -69,6 +69,14 @@ def main():
             print("%-14s C4 n=%d iters=%d early=%d: %.3f ms  %.3f Gbit/s info  mean iters %.2f  %.3e edge-it/s"
                   % (tag, n, iters, early, ms, n * 32 / ms / 1e6, it, n * 168 * it / ms * 1e3))
     c4.set_kernel(None)
+    if "methods" in which:
+        for method, name in ((0, "min-sum fp64"), (2, "bit-flip"), (3, "hard")):
+            for iters, early in ((5, True), (50, False)):
+                ms = timed(stream, lambda: c4.decode_dev(sym.data_ptr(), n * 64, n, ob.data_ptr(), os_.data_ptr(),
+                                                         oi.data_ptr(), method=method, max_iters=iters,
+                                                         early_stop=early, stream=sp))
+                print("method %d %-13s C4 n=%d iters=%d early=%d (%s kernel): %.3f ms  %.3f Gbit/s info  %.1f GB/s"
+                      % (method, name, n, iters, early, c4.kernel_name(method), ms, n * 32 / ms / 1e6, n * 518 / ms / 1e6))
     if "encode_small" in which:
         ne = 10_000_000
         d = torch.randint(0, 256, (ne, 4), dtype=torch.uint8, device="cuda", generator=gen)
