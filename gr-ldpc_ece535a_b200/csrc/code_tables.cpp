@@ -150,6 +150,82 @@ void place_checks_for_banks(CodeTables &t)
     t.bank_groups = n_groups;
 }
 
+// Shared-memory layout of the warp-per-codeword kernel.  The strip of a codeword is dc_max rows
+// of 32 words; the message of (check j, slot s) lives in row s at a bank chosen per EDGE.  Lane j
+// reads row s in the check phase; in the variable phase lane l reads the k-th edge of bit
+// l + 32 t.  Both are conflict-free iff the banks are a proper edge colouring of the bipartite
+// multigraph {slots} x {(t, k) groups} whose edges are the Tanner-graph edges -- every node has
+// degree <= 32, so 32 colours suffice (Koenig); found with the alternating-path algorithm.
+void color_warp_layout(CodeTables &t)
+{
+    const int M = t.M, N = t.N, DC = t.dc_max, DV = t.dv_max, E = t.E;
+    const int n_left = DC, n_right = 2 * DV;
+    std::vector<int> eu(E), ev(E), color(E, -1);
+    for (int j = 0; j < M; j++)
+        for (int e = t.row_ptr[j], s = 0; e < t.row_ptr[j + 1]; e++, s++) eu[e] = s;
+    for (int c = 0; c < N; c++)
+        for (int q = t.col_ptr[c], k = 0; q < t.col_ptr[c + 1]; q++, k++)
+            ev[t.edge_of_col[q]] = (c / 32) * DV + k;
+    std::vector<int> at_u((size_t)n_left * 32, -1), at_v((size_t)n_right * 32, -1);   // node, colour -> edge
+    for (int e = 0; e < E; e++) {
+        const int u = eu[e], v = ev[e];
+        int a = 0, b = 0;
+        while (at_u[u * 32 + a] >= 0) a++;          // free at u
+        while (at_v[v * 32 + b] >= 0) b++;          // free at v
+        if (a != b) {
+            // walk the a/b alternating path from v (it cannot reach u) and swap its colours
+            std::vector<int> path;
+            int node = v, col = a;
+            bool on_right = true;
+            while (true) {
+                const int f = on_right ? at_v[node * 32 + col] : at_u[node * 32 + col];
+                if (f < 0) break;
+                path.push_back(f);
+                node = on_right ? eu[f] : ev[f];
+                on_right = !on_right;
+                col = (col == a) ? b : a;
+            }
+            for (int f : path) { at_u[eu[f] * 32 + color[f]] = -1; at_v[ev[f] * 32 + color[f]] = -1; }
+            for (int f : path) {
+                color[f] = (color[f] == a) ? b : a;
+                at_u[eu[f] * 32 + color[f]] = f;
+                at_v[ev[f] * 32 + color[f]] = f;
+            }
+        }
+        color[e] = a;
+        at_u[u * 32 + a] = e;
+        at_v[v * 32 + a] = e;
+    }
+    t.w_chk_pos.assign((size_t)DC * 32, 0);
+    t.w_var_pos.assign((size_t)DV * 64, 0xFFFF);
+    t.w_pos_edge.assign((size_t)DC * 32, -1);
+    for (int s = 0; s < DC; s++) {
+        std::vector<char> used(32, 0);
+        std::vector<char> real(32, 0);
+        for (int j = 0; j < M; j++) {
+            const int e = t.row_ptr[j] + s;
+            if (e < t.row_ptr[j + 1]) {
+                t.w_chk_pos[(size_t)s * 32 + j] = (uint16_t)(s * 32 + color[e]);
+                t.w_pos_edge[(size_t)s * 32 + color[e]] = e;
+                used[color[e]] = 1;
+                real[j] = 1;
+            }
+        }
+        int nb = 0;                                  // padded slots take the banks left over in the row
+        for (int j = 0; j < 32; j++) {
+            if (real[j]) continue;
+            while (used[nb]) nb++;
+            t.w_chk_pos[(size_t)s * 32 + j] = (uint16_t)(s * 32 + nb);
+            used[nb] = 1;
+        }
+    }
+    for (int c = 0; c < N; c++)
+        for (int q = t.col_ptr[c], k = 0; q < t.col_ptr[c + 1]; q++, k++) {
+            const int e = t.edge_of_col[q];
+            t.w_var_pos[(size_t)k * 64 + c] = (uint16_t)(eu[e] * 32 + color[e]);
+        }
+}
+
 }  // namespace
 
 int build_code_tables(const int32_t *row_ptr_in, const int32_t *col_idx_in, int M, int N,
@@ -303,6 +379,7 @@ int build_code_tables(const int32_t *row_ptr_in, const int32_t *col_idx_in, int 
             for (int q = t.col_ptr[c], k = 0; q < t.col_ptr[c + 1]; q++, k++)
                 t.var_slot[(size_t)k * N + c] = (uint16_t)t.edge_slot[t.edge_of_col[q]];
     }
+    if (M <= 32 && N <= 64) color_warp_layout(t);
     return 0;
 }
 

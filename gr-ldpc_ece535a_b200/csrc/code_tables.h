@@ -37,6 +37,10 @@ struct CodeTables {
     std::vector<uint8_t> chk_deg_slot;  // [M]  degree of the check stored in column c
     int bank_extra_wavefronts = 0;      // variable-phase access groups' wavefronts beyond one
     int bank_groups = 0;
+    // warp-per-codeword kernel (M <= 32, N <= 64): conflict-free shared-memory strip layout
+    std::vector<uint16_t> w_chk_pos;    // [dc_max][32]  position of (slot s, check lane), padded slots included
+    std::vector<uint16_t> w_var_pos;    // [dv_max][64]  position of the k-th edge of a bit, or 0xFFFF
+    std::vector<int32_t> w_pos_edge;    // [dc_max*32]   position -> CSR edge id or -1 (message dumps)
     std::vector<uint8_t> chk_deg;       // [M]
     std::vector<uint8_t> var_deg;       // [N]
     std::vector<int32_t> edge_slot;     // [E]  CSR edge id -> message index (message dumps)

@@ -35,12 +35,19 @@ struct DecodeParams {
     float *dbgS;                  // scratch [n_win][E]: latest bit->check messages M (the kernels
                                   // store them as copysign(exp(-|M|), M), see spa_math.cuh)
     const int32_t *slot_edge;     // [DC][M] -> CSR edge id or -1
+    // warp kernel: conflict-free strip layout (code_tables.cpp: color_warp_layout)
+    const uint16_t *w_chk_pos;    // [DC][32]
+    const uint16_t *w_var_pos;    // [DV][64]
+    const int32_t *w_pos_edge;    // [DC*32] -> CSR edge id or -1
     // block kernel: table staging
     int stage_tables;             // 1: copy chk_var / var_slot into shared memory
     int tabA_bytes, tabB_bytes;   // padded to 16 B
 };
 
 constexpr int kWarpKernelThreads = 128;
+#ifndef WARP_MIN_BLOCKS
+#define WARP_MIN_BLOCKS 8
+#endif
 
 // decode_block_kernel shared-memory layout (host and device must agree):
 //   [0,16) mbarrier | msg[DC*M] f32 | r[N] f32 | hard[ceil(N/32)] | par[ceil(M/32)] | red[4]
@@ -85,22 +92,27 @@ __device__ __forceinline__ uint8_t pack_msb_first(uint32_t bits8)
 // warp per codeword
 // ---------------------------------------------------------------------------------
 template <int METHOD, int DC, int DV, bool DEBUG>
-__global__ void __launch_bounds__(kWarpKernelThreads)
+__global__ void __launch_bounds__(kWarpKernelThreads, WARP_MIN_BLOCKS)
 decode_warp_kernel(const DecodeParams p)
 {
     using T = msg_t<METHOD>;
     extern __shared__ __align__(16) unsigned char smem_w[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    T *msg = reinterpret_cast<T *>(smem_w) + warp * (DC * 32);   // slot-major strip: msg[s * 32 + check]
+    // strip of this warp: DC rows of 32 messages (layout: code_tables.cpp color_warp_layout), one row
+    // of per-lane dummies (writes of unused slots) and a row holding the two constants unused
+    // slots read: [0] the check update's identity, [1] zero
+    T *msg = reinterpret_cast<T *>(smem_w) + warp * ((DC + 2) * 32);
+    constexpr int kDummy = DC * 32, kPadWord = (DC + 1) * 32, kZeroWord = (DC + 1) * 32 + 1;
     const int M = p.M, N = p.N;
 
     // ---- this lane's rows/columns of H (loop invariant, registers) ----
     uint32_t row_lo = 0, row_hi = 0;                 // bits of check `lane`
-    int cdeg = 0;
+    int cdeg = 0, cpos[DC];                          // strip position of slot s of this lane's check
 #pragma unroll
     for (int s = 0; s < DC; s++) {
         const int v = (lane < M) ? p.chk_var[s * M + lane] : 0xFFFF;
+        cpos[s] = p.w_chk_pos[s * 32 + lane];
         if (v != 0xFFFF) {
             cdeg = s + 1;
             if (v < 32) row_lo |= 1u << v; else row_hi |= 1u << (v - 32);
@@ -117,14 +129,25 @@ decode_warp_kernel(const DecodeParams p)
             vpos[t][k] = 0; vchk[t][k] = 0;
             if (idx != 0xFFFF) {
                 vchk[t][k] = idx % M;
-                vpos[t][k] = (idx / M) * 32 + vchk[t][k];
+                vpos[t][k] = p.w_var_pos[k * 64 + v];
                 vdeg[t] = k + 1;
             }
         }
     }
+    // Unused slots cost no predicates in the loop: a padded check slot READS the identity word and
+    // writes its own (never read) position; an unused bit slot reads zero and writes the lane's dummy.
+    int crd[DC], vrd[2][DV], vwr[2][DV];
 #pragma unroll
-    for (int s = 0; s < DC; s++)
-        if (s >= cdeg) msg[s * 32 + lane] = pad_msg<METHOD, T>();   // padded slots, never rewritten
+    for (int s = 0; s < DC; s++) crd[s] = (s < cdeg) ? cpos[s] : kPadWord;
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int k = 0; k < DV; k++) {
+            vrd[t][k] = (k < vdeg[t]) ? vpos[t][k] : kZeroWord;
+            vwr[t][k] = (k < vdeg[t]) ? vpos[t][k] : kDummy + lane;
+        }
+    if (lane == 0) { msg[kPadWord] = pad_msg<METHOD, T>(); msg[kZeroWord] = (T)0; }
+    __syncwarp();
 
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w < p.n_win; w += warps_total) {
@@ -139,6 +162,11 @@ decode_warp_kernel(const DecodeParams p)
             const int v = lane + 32 * t;
             r[t] = (T)((ok && v < N) ? (-pol * kIn) * load_re(p, off + v) : 0.f);
         }
+        float rk[2][DV];                               // r on a real edge of the bit, 0 on an unused slot
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+            for (int k = 0; k < DV; k++) rk[t][k] = (k < vdeg[t]) ? (float)r[t] : 0.f;
         uint32_t hard0 = 0, hard1 = 0, bad = 0;
         int iters = 0;
         bool broke = false;
@@ -178,7 +206,7 @@ decode_warp_kernel(const DecodeParams p)
                 for (int k = 0; k < DV; k++)
                     if (k < vdeg[t]) {
                         if (DEBUG && p.dbgS)
-                            p.dbgS[w * p.E + p.slot_edge[(vpos[t][k] >> 5) * M + (vpos[t][k] & 31)]] = (float)r[t] * kOut;
+                            p.dbgS[w * p.E + p.w_pos_edge[vpos[t][k]]] = (float)r[t] * kOut;
                         msg[vpos[t][k]] = enc_msg<METHOD, T>(r[t]);
                     }
             iters = p.max_iters;
@@ -186,7 +214,7 @@ decode_warp_kernel(const DecodeParams p)
                 __syncwarp();
                 T m[DC];
 #pragma unroll
-                for (int s = 0; s < DC; s++) m[s] = msg[s * 32 + lane];
+                for (int s = 0; s < DC; s++) m[s] = msg[crd[s]];
                 if (DEBUG && p.dbgM && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
@@ -197,8 +225,7 @@ decode_warp_kernel(const DecodeParams p)
                 }
                 if constexpr (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC, T>(m);
 #pragma unroll
-                for (int s = 0; s < DC; s++)
-                    if (s < cdeg) msg[s * 32 + lane] = m[s];
+                for (int s = 0; s < DC; s++) msg[cpos[s]] = m[s];
                 if (DEBUG && p.dbgE && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
@@ -209,9 +236,9 @@ decode_warp_kernel(const DecodeParams p)
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
 #pragma unroll
-                    for (int k = 0; k < DV; k++) x[t][k] = msg[vpos[t][k]];
-                    if constexpr (METHOD == kMethodSpa) L[t] = var_node_spa<DV>(x[t], vdeg[t], r[t]);
-                    else L[t] = var_node_minsum<DV, T>(x[t], vdeg[t], r[t]);
+                    for (int k = 0; k < DV; k++) x[t][k] = msg[vrd[t][k]];
+                    if constexpr (METHOD == kMethodSpa) L[t] = var_node_spa_rk<DV>(x[t], rk[t]);
+                    else L[t] = var_node_minsum<DV, T>(x[t], DV, r[t]);
                 }
                 // SPA decides 1 on L <= 0 (:527), min-sum on LQ < 0 (:398)
                 const bool b0 = (lane < N) && (METHOD == kMethodSpa ? (L[0] <= (T)0) : (L[0] < (T)0));
@@ -231,11 +258,11 @@ decode_warp_kernel(const DecodeParams p)
                 for (int t = 0; t < 2; t++)
 #pragma unroll
                     for (int k = 0; k < DV; k++)
-                        if (k < vdeg[t]) {
-                            if (DEBUG && p.dbgS)
-                                p.dbgS[w * p.E + p.slot_edge[(vpos[t][k] >> 5) * M + (vpos[t][k] & 31)]] = (float)x[t][k] * kOut;
-                            msg[vpos[t][k]] = enc_msg<METHOD, T>(x[t][k]);
-                        }
+                    {
+                        if (DEBUG && p.dbgS && k < vdeg[t])
+                            p.dbgS[w * p.E + p.w_pos_edge[vpos[t][k]]] = (float)x[t][k] * kOut;
+                        msg[vwr[t][k]] = enc_msg<METHOD, T>(x[t][k]);
+                    }
             }
             // dbgM so far holds the M that ENTERED the last check step -- what the reference
             // still holds after a successful test; without one the last Step 2 counts too.

@@ -68,6 +68,8 @@ struct ldpc535_code {
     uint16_t *d_chk_var = nullptr, *d_var_slot = nullptr;
     uint8_t *d_chk_deg = nullptr;
     int32_t *d_slot_edge = nullptr;
+    uint16_t *d_w_chk_pos = nullptr, *d_w_var_pos = nullptr;   // warp kernel strip layout
+    int32_t *d_w_pos_edge = nullptr;
     uint16_t *d_var_row4 = nullptr;   // [N][4] message addresses of a bit (regular codes, dv <= 4)
     bool fits_regular = false;
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
@@ -182,6 +184,19 @@ int finish_create(ldpc535_code *c)
         }
     }
     c->fits_warp = (t.M <= 32 && t.N <= 64);
+    if (c->fits_warp) {
+        // padded to the template slot counts (rows beyond dc_max / dv_max are never used)
+        std::vector<uint16_t> cp((size_t)c->dc_t * 32, 0), vp((size_t)c->dv_t * 64, 0xFFFF);
+        std::vector<int32_t> pe((size_t)c->dc_t * 32, -1);
+        std::copy(t.w_chk_pos.begin(), t.w_chk_pos.end(), cp.begin());
+        std::copy(t.w_var_pos.begin(), t.w_var_pos.end(), vp.begin());
+        std::copy(t.w_pos_edge.begin(), t.w_pos_edge.end(), pe.begin());
+        for (int s = t.dc_max; s < c->dc_t; s++)
+            for (int l = 0; l < 32; l++) cp[(size_t)s * 32 + l] = (uint16_t)(s * 32 + l);
+        if ((st = upload(&c->d_w_chk_pos, cp.data(), cp.size() * 2, cp.size() * 2))) return st;
+        if ((st = upload(&c->d_w_var_pos, vp.data(), vp.size() * 2, vp.size() * 2))) return st;
+        if ((st = upload(&c->d_w_pos_edge, pe.data(), pe.size() * 4, pe.size() * 4))) return st;
+    }
     c->is_c4 = tables_match_c4(t);
     const size_t fixed = block_smem_fixed_bytes(c->dc_t, t.M, t.N);
     const size_t staged = fixed + c->tabA_bytes + c->tabB_bytes;
@@ -212,7 +227,7 @@ void release(ldpc535_code *c)
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
-    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_var_row4);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_var_row4); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
     delete c;
 }
 
@@ -226,11 +241,15 @@ int family_from_name(const char *name, int *out)
     return 1;
 }
 
-int resolve_family(const ldpc535_code *c, int forced, int method)
+// early_stop: the thread-per-codeword kernel stops a whole 256-codeword CTA together, so with
+// early stop its time does not drop when frames converge early; the warp-per-codeword kernel
+// stops each codeword on its own (measured on B200, 5 iterations max: equal at 2 dB, warp kernel
+// 1.1x / 1.5x / 2x faster at 4 / 6 / 8 dB; profiles/r1_microbench.txt).
+int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop = 0)
 {
     int f = forced;
     if (f == kAuto) {
-        if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT) f = kC4Thread;
+        if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && !early_stop) f = kC4Thread;
         else if (c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT) f = kRegular;
         else if (c->fits_warp) f = kWarp;
         else f = kBlock;
@@ -250,7 +269,7 @@ template <int METHOD, int DC, int DV, bool DBG>
 cudaError_t launch_warp(const ldpc535_code *c, const DecodeParams &p, cudaStream_t st)
 {
     const int wpb = kWarpKernelThreads / 32;
-    const size_t smem = sizeof(msg_t<METHOD>) * wpb * DC * 32;
+    const size_t smem = sizeof(msg_t<METHOD>) * wpb * (DC + 2) * 32;
     long long blocks = (p.n_win + wpb - 1) / wpb;
     const int grid = (int)std::min<long long>(blocks, (long long)c->sm_count * 16);
     decode_warp_kernel<METHOD, DC, DV, DBG><<<grid, kWarpKernelThreads, smem, st>>>(p);
@@ -304,13 +323,14 @@ cudaError_t launch_generic(const ldpc535_code *c, int family, int method, bool d
 int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParams p, cudaStream_t st)
 {
     method = norm_method(method);
-    int family = resolve_family(c, forced, method);
+    int family = resolve_family(c, forced, method, p.early_stop);
     if (family < 0) return fail(LDPC535_ERR_UNSUPPORTED, "kernel family not available for this code/method");
     if (p.n_win == 0) return LDPC535_OK;
     p.M = c->t.M; p.N = c->t.N; p.K = c->t.K; p.E = c->t.E;
     p.nbytes = (c->t.K + 7) / 8;
     p.chk_var = c->d_chk_var; p.var_slot = c->d_var_slot; p.chk_deg = c->d_chk_deg;
     p.slot_edge = c->d_slot_edge;
+    p.w_chk_pos = c->d_w_chk_pos; p.w_var_pos = c->d_w_var_pos; p.w_pos_edge = c->d_w_pos_edge;
     p.stage_tables = c->stage_tables; p.tabA_bytes = c->tabA_bytes; p.tabB_bytes = c->tabB_bytes;
     cudaError_t e;
     if (family == kRegular && dbg) family = kBlock;            // message dumps live in the generic kernel

@@ -141,6 +141,32 @@ __device__ __forceinline__ void check_node_minsum(T (&m)[DC])
 //   L   = q_0 + q_1 + ...            (lib/ldpc_decoder_cb_impl.cc:519-525)
 //   M_k = sum_{p != k} q_p            (:540-553)
 // as prefix + suffix sums; for dv <= 3 this is the reference's own order of additions.
+// Same update with a per-edge intrinsic value rk[k] (r on a real edge, 0 on an unused slot whose
+// x[k] reads as 0): no degree predicates -- an unused slot contributes q = 0 like above and its
+// outgoing message goes to a dummy location.
+template <int DV>
+__device__ __forceinline__ float var_node_spa_rk(float (&x)[DV], const float (&rk)[DV])
+{
+    float q[DV], pre[DV], suf[DV];
+#pragma unroll
+    for (int k = 0; k < DV; k++) q[k] = x[k] + rk[k];
+    pre[0] = q[0];
+#pragma unroll
+    for (int k = 1; k < DV; k++) pre[k] = pre[k - 1] + q[k];
+    suf[DV - 1] = q[DV - 1];
+#pragma unroll
+    for (int k = DV - 2; k >= 0; k--) suf[k] = q[k] + suf[k + 1];
+    if constexpr (DV == 1) {
+        x[0] = 0.f;
+    } else {
+        x[0] = suf[1];
+        x[DV - 1] = pre[DV - 2];
+#pragma unroll
+        for (int k = 1; k < DV - 1; k++) x[k] = pre[k - 1] + suf[k + 1];
+    }
+    return pre[DV - 1];
+}
+
 template <int DV>
 __device__ __forceinline__ float var_node_spa(float (&x)[DV], int dv, float r)
 {
