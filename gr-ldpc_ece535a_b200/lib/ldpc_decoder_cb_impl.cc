@@ -47,7 +47,7 @@ int device_from_env()
 }
 // How far the batcher speculates on a miss.
 const long kTrackBatch = 1 << 16;   // frames at the frame stride
-const long kSearchBatch = 64;       // offsets, each in both polarities
+const long kSearchBatch = 256;      // offsets, each in both polarities (a failed search costs one GPU call per 256 slides)
 }  // namespace
 
 ldpc_decoder_cb::sptr ldpc_decoder_cb::make(const int method)

@@ -1,0 +1,123 @@
+#!/usr/bin/env python3
+"""BASELINE.json's other configurations, measured (bench.py covers configs[2] and, under
+torch.distributed.run, configs[4]):
+
+  config 1  shipped 32x64 code, 1 000 codewords encode -> BPSK+AWGN -> sum-product (5 iterations,
+            early stop: the reference defaults): bit-exact check against the CPU oracle + time
+  config 2  headless transmitter/receiver chain (examples/headless_txrx.py) on an image-sized
+            file, Eb/N0 0..4 dB: BER, sync events, wall time
+  config 4  (3,6)-regular n = 8192 code, early termination on, batch sweep 1 k .. 1 M codewords
+
+Prints a markdown report (stdout); needs a B200."""
+import ctypes as C
+import importlib.util
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "gr-ldpc_ece535a_b200", "python"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np          # noqa: E402
+import torch                # noqa: E402
+import ldpc_ece535a as L    # noqa: E402
+from oracle import oracle as O   # noqa: E402
+
+
+def config1():
+    print("## config 1 -- 32x64 code, 1 000 codewords, 5 iterations, early stop (reference defaults)\n")
+    print("| Eb/N0 | frames identical to the oracle (bytes, iterations, syndrome weight) | frame errors | mean iterations | GPU ms (host buffers) | CPU oracle ms (1 thread) |")
+    print("|---|---|---|---|---|---|")
+    codes = O.load_ref_codes()
+    Hp, Lm, Um, _ = O.reorder_h(codes["shipped"]["H"])
+    c4 = L.Code(None, device=0)
+    for ebn0 in (None, 0.0, 2.0, 4.0, 6.0):
+        rng = np.random.default_rng(1000 + int(ebn0 or 0))
+        data = rng.integers(0, 256, (1000, 4)).astype(np.uint8)
+        sym = c4.encode(data)
+        want_sym, _ = O.encoder_work(Hp, Lm, Um, data.reshape(-1), 64000)
+        assert np.array_equal(sym.reshape(-1), want_sym)
+        if ebn0 is not None:
+            sym.real += rng.standard_normal(sym.shape, dtype=np.float32) * np.float32(np.sqrt(10.0 ** (-ebn0 / 10.0)))
+        c4.decode(sym, method=1)
+        t0 = time.perf_counter()
+        b, sy, it = c4.decode(sym, method=1)
+        t_gpu = (time.perf_counter() - t0) * 1e3
+        wb, wit, wsy, dt = O.decode_frames(sym, Hp, method=1, iterations=5, early_stop=True, threads=1)
+        same = int(((b == wb).all(axis=1) & (it == wit) & (sy == wsy)).sum())
+        print("| %s | %d / 1000 | %d | %.2f | %.3f | %.1f |" % ("noiseless" if ebn0 is None else "%.0f dB" % ebn0, same,
+              int((b != data).any(axis=1).sum()), it.mean(), t_gpu, dt * 1e3))
+    print()
+
+
+def config2():
+    print("## config 2 -- headless transmitter/receiver chain, 19 268-byte image sent twice, sum-product block\n")
+    spec = importlib.util.spec_from_file_location("headless_txrx", os.path.join(ROOT, "examples", "headless_txrx.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from test_image_sink import bmp
+    image = bmp(19268, 77)
+    payload = np.tile(image, 2)
+    print("| Eb/N0 | decoded bytes | byte errors | BER | sync events (1 in, 2 inverted, 3 lost) | files written | GPU batches / windows | wall ms |")
+    print("|---|---|---|---|---|---|---|---|")
+    for ebn0 in (None, 0.0, 1.0, 2.0, 3.0, 4.0):
+        r = mod.run_chain(payload, ebn0, 1, out_path="/tmp/result_cfg2.bmp", buf_frames=4096)
+        d = r["decoded"]
+        n = min(d.size, payload.size)
+        be = int((d[:n] != payload[:n]).sum())
+        bit = int(np.unpackbits(d[:n] ^ payload[:n]).sum())
+        ev = r["events"]
+        print("| %s | %d | %d | %.3e | %s%s | %d | %d / %d | %.1f |" % (
+            "noiseless" if ebn0 is None else "%.0f dB" % ebn0, d.size, be, bit / max(8 * n, 1), ev[:8],
+            "..." if len(ev) > 8 else "", r["files"], r["state"]["gpu_batches"], r["state"]["gpu_windows"], r["seconds"] * 1e3))
+    print("\n(byte errors are counted position by position against the sent stream; once the block loses sync the\n"
+          "streams shift, so at 0-2 dB the figure mostly measures that shift -- the GPU tests check the stream is\n"
+          "identical to the reference's state machine at every Eb/N0.)\n")
+
+
+def config4():
+    print("## config 4 -- (3,6)-regular n = 8192 code (seeded generator), early termination on, 50 iterations max, Eb/N0 = 2 dB\n")
+    c8, seed = L.codes.first_invertible(n=8192, seed=535, device=0)
+    print("code seed %d, kernel `%s`\n" % (seed, c8.kernel_name()))
+    print("| batch (codewords) | device-resident ms | Gbit/s info | edge-iterations/s | mean iterations | frames recovered |")
+    print("|---|---|---|---|---|---|")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    from profile_kernels import synth, timed
+    nmax = 1_000_000
+    chunk = 50_000
+    data = torch.empty((nmax, 512), dtype=torch.uint8, device="cuda")
+    sym = torch.empty((nmax, 8192, 2), dtype=torch.float32, device="cuda")
+    for a in range(0, nmax, chunk):
+        d, s = synth(c8, chunk, 2.0, sp, gen)
+        data[a:a + chunk] = d
+        sym[a:a + chunk] = s
+    del d, s
+    ob = torch.empty((nmax, 512), dtype=torch.uint8, device="cuda")
+    os_ = torch.empty(nmax, dtype=torch.uint8, device="cuda")
+    oi = torch.empty(nmax, dtype=torch.uint8, device="cuda")
+    for n in (1000, 10_000, 100_000, 1_000_000):
+        ms = timed(stream, lambda: c8.decode_dev(sym.data_ptr(), n * 8192, n, ob.data_ptr(), os_.data_ptr(), oi.data_ptr(),
+                                                 max_iters=50, early_stop=True, stream=sp), reps=1 if n >= 100_000 else 3)
+        it = oi[:n].float().mean().item()
+        okf = (ob[:n] == data[:n]).all(dim=1).float().mean().item()
+        print("| %d | %.3f | %.2f | %.3e | %.2f | %.5f |" % (n, ms, n * 4096 / ms / 1e6, n * 24576 * it / ms * 1e3, it, okf))
+    # encoder
+    ms = timed(stream, lambda: c8.encode_dev(data.data_ptr(), 200_000, sym.data_ptr(), stream=sp))
+    print("\nencoder, 200 000 frames device-resident: %.3f ms, %.1f GB/s, %.1f Gbit/s info\n" % (ms, 200_000 * 66048 / ms / 1e6, 200_000 * 4096 / ms / 1e6))
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    info = L.device_info(0)
+    print("# BASELINE configurations 1, 2, 4 on %s (tools/run_configs.py)\n" % info["name"])
+    which = sys.argv[1:] or ["1", "2", "4"]
+    if "1" in which:
+        config1()
+    if "2" in which:
+        config2()
+    if "4" in which:
+        config4()
