@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "code_tables.h"
@@ -855,6 +856,106 @@ int ldpc535_decode_debug(ldpc535_code *c, const float *sym, size_t n_win, int ma
     CUX(cudaStreamSynchronize(c->stream));
 #undef CUX
     cleanup();
+    return LDPC535_OK;
+}
+
+}  // extern "C"
+
+// ===================================================================================
+// several GPUs from one process: contiguous shards, one host thread per device
+struct ldpc535_pool {
+    std::vector<ldpc535_code *> codes;
+};
+
+extern "C" {
+
+int ldpc535_pool_create(const int32_t *H, int M, int N, const int *devices, int n_devices, ldpc535_pool **out)
+{
+    if (!out || !devices || n_devices < 1) return fail(LDPC535_ERR_INVALID, "bad pool arguments");
+    *out = nullptr;
+    ldpc535_pool *p = new (std::nothrow) ldpc535_pool();
+    if (!p) return fail(LDPC535_ERR_NOMEM, "out of host memory");
+    for (int i = 0; i < n_devices; i++) {
+        ldpc535_code *c = nullptr;
+        const int st = H ? ldpc535_code_create(H, M, N, devices[i], &c) : ldpc535_code_create_default(devices[i], &c);
+        if (st) {
+            const std::string msg = g_last_error;
+            ldpc535_pool_destroy(p);
+            return fail(st, msg);
+        }
+        p->codes.push_back(c);
+    }
+    *out = p;
+    return LDPC535_OK;
+}
+
+void ldpc535_pool_destroy(ldpc535_pool *p)
+{
+    if (!p) return;
+    for (ldpc535_code *c : p->codes) ldpc535_code_destroy(c);
+    delete p;
+}
+
+int ldpc535_pool_size(const ldpc535_pool *p) { return p ? (int)p->codes.size() : 0; }
+
+ldpc535_code *ldpc535_pool_code(ldpc535_pool *p, int i)
+{
+    return (p && i >= 0 && i < (int)p->codes.size()) ? p->codes[i] : nullptr;
+}
+
+int ldpc535_pool_decode_batch(ldpc535_pool *p, const float *sym, size_t n_sym, const int64_t *win_offset,
+                              const int8_t *polarity, size_t n_win, int method, int max_iters, int early_stop,
+                              int synd_threshold, uint8_t *out_bytes, uint8_t *out_synd, uint8_t *out_iters)
+{
+    if (!p || p->codes.empty()) return fail(LDPC535_ERR_INVALID, "pool is NULL");
+    const size_t g = p->codes.size();
+    const size_t N = (size_t)p->codes[0]->t.N, nb = (size_t)(p->codes[0]->t.K + 7) / 8;
+    if (!win_offset && n_win * N > n_sym) return fail(LDPC535_ERR_INVALID, "n_win * N exceeds n_sym");
+    const size_t per = (n_win + g - 1) / g;
+    std::vector<int> status(g, LDPC535_OK);
+    std::vector<std::string> errors(g);
+    std::vector<std::thread> threads;
+    for (size_t i = 0; i < g; i++) {
+        const size_t lo = std::min(n_win, i * per), hi = std::min(n_win, (i + 1) * per);
+        if (hi <= lo) continue;
+        threads.emplace_back([=, &status, &errors]() {
+            // aligned frames: hand the shard its own slice of the symbol buffer; window lists keep
+            // absolute offsets into the whole buffer
+            const float *s = win_offset ? sym : sym + lo * N * 2;
+            const size_t ns = win_offset ? n_sym : (hi - lo) * N;
+            status[i] = ldpc535_decode_batch(p->codes[i], s, ns, win_offset ? win_offset + lo : nullptr,
+                                             polarity ? polarity + lo : nullptr, hi - lo, method, max_iters,
+                                             early_stop, synd_threshold, out_bytes + lo * nb,
+                                             out_synd ? out_synd + lo : nullptr, out_iters ? out_iters + lo : nullptr);
+            if (status[i]) errors[i] = g_last_error;          // thread-local: copy it out
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (size_t i = 0; i < g; i++)
+        if (status[i]) return fail(status[i], errors[i]);
+    return LDPC535_OK;
+}
+
+int ldpc535_pool_encode_batch(ldpc535_pool *p, const uint8_t *in, size_t n_frames, float *out)
+{
+    if (!p || p->codes.empty()) return fail(LDPC535_ERR_INVALID, "pool is NULL");
+    const size_t g = p->codes.size();
+    const size_t N = (size_t)p->codes[0]->t.N, nb = (size_t)(p->codes[0]->t.K + 7) / 8;
+    const size_t per = (n_frames + g - 1) / g;
+    std::vector<int> status(g, LDPC535_OK);
+    std::vector<std::string> errors(g);
+    std::vector<std::thread> threads;
+    for (size_t i = 0; i < g; i++) {
+        const size_t lo = std::min(n_frames, i * per), hi = std::min(n_frames, (i + 1) * per);
+        if (hi <= lo) continue;
+        threads.emplace_back([=, &status, &errors]() {
+            status[i] = ldpc535_encode_batch(p->codes[i], in + lo * nb, hi - lo, out + lo * N * 2);
+            if (status[i]) errors[i] = g_last_error;
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (size_t i = 0; i < g; i++)
+        if (status[i]) return fail(status[i], errors[i]);
     return LDPC535_OK;
 }
 

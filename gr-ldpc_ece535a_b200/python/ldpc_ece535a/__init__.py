@@ -8,9 +8,9 @@ There is no CPU path: importing works anywhere, computing needs libldpc535.so an
 """
 from ._abi import (METHOD_BITFLIP, METHOD_HARD, METHOD_LOGDOMAIN, METHOD_SUMPRODUCT, LIB_PATH,
                    Ldpc535Error)
-from .code import Code, device_count, device_info
+from .code import Code, Pool, device_count, device_info
 from .blocks import image_sink, ldpc_decoder_cb, ldpc_encoder_bc
 from . import codes
 
-__all__ = ["ldpc_decoder_cb", "ldpc_encoder_bc", "image_sink", "Code", "codes", "device_count", "device_info", "Ldpc535Error", "LIB_PATH",
+__all__ = ["ldpc_decoder_cb", "ldpc_encoder_bc", "image_sink", "Code", "Pool", "codes", "device_count", "device_info", "Ldpc535Error", "LIB_PATH",
            "METHOD_LOGDOMAIN", "METHOD_SUMPRODUCT", "METHOD_BITFLIP", "METHOD_HARD"]

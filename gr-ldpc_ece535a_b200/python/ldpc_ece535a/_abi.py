@@ -33,6 +33,12 @@ SYMBOLS = {
     "ldpc535_code_kernel_name": (C.c_char_p, [_vp, _i]),
     "ldpc535_code_set_kernel": (_i, [_vp, C.c_char_p]),
     "ldpc535_launch_count": (_u64, [_vp]),
+    "ldpc535_pool_create": (_i, [_vp, _i, _i, _pi, _i, C.POINTER(_vp)]),
+    "ldpc535_pool_destroy": (None, [_vp]),
+    "ldpc535_pool_size": (_i, [_vp]),
+    "ldpc535_pool_code": (_vp, [_vp, _i]),
+    "ldpc535_pool_decode_batch": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ldpc535_pool_encode_batch": (_i, [_vp, _vp, _sz, _vp]),
     "ldpc535_code_host_path": (_i, [_vp, _pi, _pi]),
     "ldpc535_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "ldpc535_host_free": (_i, [_vp]),

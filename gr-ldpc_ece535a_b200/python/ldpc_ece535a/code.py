@@ -167,6 +167,54 @@ class Code:
         check(lib().ldpc535_stream_sync(self._h, stream), "stream_sync")
 
 
+class Pool:
+    """Several GPUs from one process (ldpc535_pool): contiguous shards, one host thread per
+    device, host-side gather.  devices may repeat (two handles on one GPU)."""
+
+    def __init__(self, devices, H=None):
+        self._p = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        if H is None:
+            check(lib().ldpc535_pool_create(None, 0, 0, devs, len(devices), C.byref(self._p)), "pool_create")
+        else:
+            Hd = np.ascontiguousarray(H, np.int32)
+            check(lib().ldpc535_pool_create(_ptr(Hd), Hd.shape[0], Hd.shape[1], devs, len(devices),
+                                            C.byref(self._p)), "pool_create")
+        m, n, k = C.c_int(), C.c_int(), C.c_int()
+        check(lib().ldpc535_code_info(lib().ldpc535_pool_code(self._p, 0), m, n, k, None, None), "code_info")
+        self.M, self.N, self.K = m.value, n.value, k.value
+        self.nbytes = (self.K + 7) // 8
+        self.size = lib().ldpc535_pool_size(self._p)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().ldpc535_pool_destroy(self._p)
+            self._p = None
+
+    __del__ = close
+
+    def encode(self, data_bytes):
+        data = np.ascontiguousarray(data_bytes, np.uint8).reshape(-1)
+        n = data.size // self.nbytes
+        out = np.empty((n, self.N), np.complex64)
+        check(lib().ldpc535_pool_encode_batch(self._p, _ptr(data), n, _ptr(out)), "pool_encode_batch")
+        return out
+
+    def decode(self, sym, method=_abi.METHOD_SUMPRODUCT, max_iters=5, early_stop=True, win_offset=None,
+               polarity=None):
+        sym = np.ascontiguousarray(sym, np.complex64).reshape(-1)
+        off = None if win_offset is None else np.ascontiguousarray(win_offset, np.int64)
+        pol = None if polarity is None else np.ascontiguousarray(polarity, np.int8)
+        n_win = sym.size // self.N if off is None else off.size
+        ob = np.empty((n_win, self.nbytes), np.uint8)
+        os_ = np.empty(n_win, np.uint8)
+        oi = np.empty(n_win, np.uint8)
+        check(lib().ldpc535_pool_decode_batch(self._p, _ptr(sym), sym.size, _ptr(off), _ptr(pol), n_win,
+                                              int(method), int(max_iters), int(bool(early_stop)), self.M // 8,
+                                              _ptr(ob), _ptr(os_), _ptr(oi)), "pool_decode_batch")
+        return ob, os_, oi
+
+
 def device_count():
     n = C.c_int()
     check(lib().ldpc535_device_count(n), "device_count")

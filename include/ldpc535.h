@@ -201,6 +201,26 @@ LDPC535_API int ldpc535_code_set_kernel(ldpc535_code *code, const char *kernel);
  * override). */
 LDPC535_API int ldpc535_code_host_path(const ldpc535_code *code, int *pack_pinned, int *pack_threads);
 
+/* ---- several GPUs from one host process -------------------------------------- */
+/* Codewords are independent, so a batch is cut into contiguous shards, one per device, each
+ * decoded / encoded by that device's own handle from its own host thread, every shard writing
+ * its slice of the caller's output arrays (a host-side gather; there is no inter-GPU traffic
+ * and no collective).  devices[i] may repeat (two handles on one GPU). */
+typedef struct ldpc535_pool ldpc535_pool;
+LDPC535_API int ldpc535_pool_create(const int32_t *H, int M, int N, const int *devices, int n_devices,
+                                    ldpc535_pool **out);            /* H == NULL: the 32x64 default code */
+LDPC535_API void ldpc535_pool_destroy(ldpc535_pool *pool);
+LDPC535_API int ldpc535_pool_size(const ldpc535_pool *pool);
+LDPC535_API ldpc535_code *ldpc535_pool_code(ldpc535_pool *pool, int i);
+/* Same arguments and results as ldpc535_decode_batch / ldpc535_encode_batch. */
+LDPC535_API int ldpc535_pool_decode_batch(ldpc535_pool *pool, const float *sym, size_t n_sym,
+                                          const int64_t *win_offset, const int8_t *polarity,
+                                          size_t n_win, int method, int max_iters, int early_stop,
+                                          int synd_threshold, uint8_t *out_bytes, uint8_t *out_synd,
+                                          uint8_t *out_iters);
+LDPC535_API int ldpc535_pool_encode_batch(ldpc535_pool *pool, const uint8_t *in, size_t n_frames,
+                                          float *out);
+
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 LDPC535_API uint64_t ldpc535_launch_count(const ldpc535_code *code);
 

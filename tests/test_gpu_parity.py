@@ -518,3 +518,28 @@ def test_config3_full_size_round_trip(c4):
     c4.decode_dev(sym2.data_ptr(), n * 64, n, ob.data_ptr(), os_.data_ptr(), oi.data_ptr())
     c4.sync()
     assert bool((ob == (d ^ d2)).all()) and int(os_.max()) == 0
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0]])
+def test_pool_shards_and_gathers(c4, devices):
+    """ldpc535_pool: contiguous shards over several handles (here on one GPU; on a multi-GPU box
+    list every device), host-side gather; results equal the single-handle call."""
+    if L.device_count() > 1 and len(devices) > 1:
+        devices = [i % L.device_count() for i in range(len(devices))]
+    pool = L.Pool(devices)
+    assert pool.size == len(devices)
+    rng = np.random.default_rng(21)
+    for n in (0, 1, 2, 1001):
+        data = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+        sym = pool.encode(data)
+        assert np.array_equal(sym, c4.encode(data))
+        noisy = sym.copy()
+        noisy.real += rng.standard_normal(sym.shape, dtype=np.float32) * np.float32(0.7)
+        for a, b in zip(pool.decode(noisy), c4.decode(noisy)):
+            assert np.array_equal(a, b)
+    stream = noisy.reshape(-1)
+    offs = rng.integers(0, stream.size - 63, 777).astype(np.int64)
+    pol = rng.choice(np.array([-1, 1], np.int8), 777)
+    for a, b in zip(pool.decode(stream, win_offset=offs, polarity=pol), c4.decode(stream, win_offset=offs, polarity=pol)):
+        assert np.array_equal(a, b)
+    pool.close()
