@@ -22,14 +22,18 @@ __host__ __device__ inline size_t regular_smem_bytes(int dc, int M, int N)
     return b + 8 * (size_t)N;
 }
 
-template <int DC, int DV>
+// MF, NF > 0: code size fixed at compile time (1024 threads): every stride is an immediate and
+// the per-thread loops (MF/1024 checks, NF/1024 bits) unroll without bounds checks.  0: run-time.
+template <int DC, int DV, int MF = 0, int NF = 0>
 __global__ void __launch_bounds__(1024, 1)
 decode_regular_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row4)
 {
     static_assert(DV <= 4, "the packed bit table holds four addresses");
+    static_assert(MF % 1024 == 0 && NF % 1024 == 0, "fixed sizes are whole multiples of the CTA");
+    constexpr bool kFixed = MF > 0 && NF > 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int M = p.M, N = p.N;
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int M = kFixed ? MF : p.M, N = kFixed ? NF : p.N;
+    const int tid = threadIdx.x, nt = kFixed ? 1024 : (int)blockDim.x, lane = tid & 31;
     const int nwords = (N + 31) >> 5;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     float *msg = reinterpret_cast<float *>(smem_raw + 16);
@@ -87,13 +91,19 @@ decode_regular_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row
         for (int h = 0; h < p.max_iters; h++) {
             // ---- check nodes (+ parity of the previous iteration's decisions from the tags) ----
             uint32_t tagbad = 0;
-            for (int j = tid; j < M; j += nt) {
+            auto do_check = [&](int j) {
                 float m[DC];
 #pragma unroll
                 for (int s = 0; s < DC; s++) m[s] = msg[s * M + j];
                 tagbad |= check_node_spa<DC, true>(m);
 #pragma unroll
                 for (int s = 0; s < DC; s++) msg[s * M + j] = m[s];
+            };
+            if constexpr (kFixed) {
+#pragma unroll
+                for (int q = 0; q < MF / 1024; q++) do_check(q * 1024 + tid);
+            } else {
+                for (int j = tid; j < M; j += nt) do_check(j);
             }
             if (tag) {
                 const int bad = __syncthreads_or((int)(tagbad & 0x40000000u));
@@ -102,24 +112,35 @@ decode_regular_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row
                 __syncthreads();
             }
             // ---- variable nodes: L, hard decision, next messages (tagged with the decision) ----
-            for (int base = 0; base < N; base += nt) {
-                const int i = base + tid;
-                bool b = false;
-                if (i < N) {
-                    const uint2 a = vt[i];
-                    int idx[4] = {(int)(a.x & 0xffffu), (int)(a.x >> 16), (int)(a.y & 0xffffu), (int)(a.y >> 16)};
-                    float x[DV];
+            const uint32_t tagmask = tag ? 0x40000000u : 0u;
+            auto do_var = [&](int i) -> bool {
+                const uint2 a = vt[i];
+                int idx[4] = {(int)(a.x & 0xffffu), (int)(a.x >> 16), (int)(a.y & 0xffffu), (int)(a.y >> 16)};
+                float x[DV];
 #pragma unroll
-                    for (int k = 0; k < DV; k++) x[k] = msg[idx[k]];
-                    const float L = var_node_spa<DV>(x, DV, r[i]);
-                    b = (L <= 0.f);
-                    const uint32_t tagbit = (tag && b) ? 0x40000000u : 0u;
+                for (int k = 0; k < DV; k++) x[k] = msg[idx[k]];
+                const float L = var_node_spa<DV>(x, DV, r[i]);
+                const bool b = (L <= 0.f);
+                const uint32_t tagbit = b ? tagmask : 0u;
 #pragma unroll
-                    for (int k = 0; k < DV; k++)
-                        msg[idx[k]] = __uint_as_float(__float_as_uint(to_check_msg(x[k])) | tagbit);
+                for (int k = 0; k < DV; k++)
+                    msg[idx[k]] = __uint_as_float(__float_as_uint(to_check_msg(x[k])) | tagbit);
+                return b;
+            };
+            if constexpr (kFixed) {
+#pragma unroll
+                for (int q = 0; q < NF / 1024; q++) {
+                    const int i = q * 1024 + tid;
+                    const uint32_t wd = __ballot_sync(0xffffffffu, do_var(i));
+                    if (lane == 0) hard[i >> 5] = wd;
                 }
-                const uint32_t wd = __ballot_sync(0xffffffffu, b);
-                if (lane == 0 && i < N) hard[i >> 5] = wd;
+            } else {
+                for (int base = 0; base < N; base += nt) {
+                    const int i = base + tid;
+                    const bool b = (i < N) ? do_var(i) : false;
+                    const uint32_t wd = __ballot_sync(0xffffffffu, b);
+                    if (lane == 0 && i < N) hard[i >> 5] = wd;
+                }
             }
             __syncthreads();
         }

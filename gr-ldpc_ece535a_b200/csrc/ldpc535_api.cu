@@ -336,7 +336,9 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
     cudaError_t e;
     if (family == kRegular && dbg) family = kBlock;            // message dumps live in the generic kernel
     if (family == kRegular) {
-        auto kern = decode_regular_kernel<6, 3>;
+        // BASELINE config 4's size gets the fully unrolled instantiation
+        const bool fixed8k = c->t.M == 4096 && c->t.N == 8192 && c->block_threads == 1024;
+        auto kern = fixed8k ? decode_regular_kernel<6, 3, 4096, 8192> : decode_regular_kernel<6, 3>;
         const size_t smem = regular_smem_bytes(6, c->t.M, c->t.N);
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {
