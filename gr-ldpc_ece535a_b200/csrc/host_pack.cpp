@@ -32,6 +32,13 @@ void pack_range(const float *__restrict src, float *__restrict dst, size_t n)
 }
 }  // namespace
 
+int host_sharing_ranks()
+{
+    for (const char *name : {"LOCAL_WORLD_SIZE", "WORLD_SIZE"})
+        if (const char *s = std::getenv(name)) return std::max(1, std::atoi(s));
+    return 1;
+}
+
 int default_pack_threads()
 {
     if (const char *s = std::getenv("LDPC535_PACK_THREADS")) {
@@ -43,9 +50,7 @@ int default_pack_threads()
     unsigned hc = std::thread::hardware_concurrency();
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) hc = (unsigned)CPU_COUNT(&set);
-    unsigned ranks = 1;
-    for (const char *name : {"LOCAL_WORLD_SIZE", "WORLD_SIZE"})
-        if (const char *s = std::getenv(name)) { ranks = (unsigned)std::max(1, std::atoi(s)); break; }
+    const unsigned ranks = (unsigned)host_sharing_ranks();
     return (int)std::max(1u, std::min(32u, hc / ranks));
 }
 

@@ -10,4 +10,6 @@ namespace ldpc535 {
 // dst[i] = src[2 * i] for i < n, split over `threads` workers (>= 1).
 void pack_real_parts(const float *src_interleaved, float *dst, size_t n, int threads);
 int default_pack_threads();
+// ranks of a one-process-per-GPU job sharing this host (LOCAL_WORLD_SIZE / WORLD_SIZE), >= 1
+int host_sharing_ranks();
 }  // namespace ldpc535

@@ -86,9 +86,11 @@ struct ldpc535_code {
     bool slots_ready = false;
     bool stage_ready = false;
     int pack_threads = 1;
-    int pack_pinned = 0;          // pack even when the caller's buffer is pinned: LDPC535_PACK_PINNED=1,
-                                  // or by default when this handle has >= 8 packing threads (measured
-                                  // on the B200 box per 5.12 GB: 8 threads 89 ms, 12+ threads 76 ms, raw PCIe 94 ms)
+    int pack_pinned = 0;          // pack even when the caller's buffer is pinned: LDPC535_PACK_PINNED=1, or by
+                                  // default when this handle is the only one feeding from this host and has
+                                  // >= 8 packing threads.  Measured per 5.12 GB on B200 boxes: one GPU, 16
+                                  // cores: 8 threads 89 ms, 12+ threads 76 ms, raw PCIe 94 ms; four ranks on
+                                  // 32 cores: packing 220 ms (host memory traffic doubles), raw PCIe 101 ms.
     size_t max_win_per_chunk = 0;
     Slot slots[kSlots];
     uint64_t launches = 0;
@@ -136,7 +138,7 @@ int finish_create(ldpc535_code *c)
                                                std::to_string(prop.minor) + ", kernels are built for sm_100a");
     c->sm_count = prop.multiProcessorCount;
     c->pack_threads = default_pack_threads();
-    c->pack_pinned = c->pack_threads >= 8;
+    c->pack_pinned = c->pack_threads >= 8 && host_sharing_ranks() == 1;
     if (const char *e = getenv("LDPC535_PACK_PINNED")) c->pack_pinned = atoi(e) != 0;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -887,6 +889,11 @@ int ldpc535_pool_create(const int32_t *H, int M, int N, const int *devices, int 
         }
         p->codes.push_back(c);
     }
+    if (n_devices > 1)                      // the handles share this host: split the packing threads,
+        for (ldpc535_code *c : p->codes) {  // leave pinned input to the copy engines
+            c->pack_threads = std::max(1, c->pack_threads / n_devices);
+            c->pack_pinned = 0;
+        }
     *out = p;
     return LDPC535_OK;
 }

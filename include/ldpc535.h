@@ -197,8 +197,9 @@ LDPC535_API int ldpc535_code_set_kernel(ldpc535_code *code, const char *kernel);
  * through pinned memory by `pack_threads` host threads that copy only the REAL parts (the
  * decoder never reads the imaginary ones), halving the PCIe bytes; *pack_pinned != 0 means
  * pinned input is packed the same way instead of being handed to the copy engine as it is
- * (default when >= 8 threads are available; LDPC535_PACK_PINNED / LDPC535_PACK_THREADS
- * override). */
+ * (default when >= 8 threads are available and no other rank / pool handle feeds from the same
+ * host -- with several GPUs the host memory traffic of packing costs more than the PCIe bytes
+ * it saves; LDPC535_PACK_PINNED / LDPC535_PACK_THREADS override). */
 LDPC535_API int ldpc535_code_host_path(const ldpc535_code *code, int *pack_pinned, int *pack_threads);
 
 /* ---- several GPUs from one host process -------------------------------------- */
