@@ -19,6 +19,7 @@
 #include "decode_kernels.cuh"
 #include "decode_c4_kernel.cuh"
 #include "decode_regular_kernel.cuh"
+#include "decode_hard_kernel.cuh"
 #include "encode_kernels.cuh"
 #include "host_pack.h"
 #include "ldpc535_default_code.h"
@@ -42,7 +43,7 @@ int fail(int status, const std::string &msg)
             return fail(LDPC535_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4 };
+enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4, kHard64 = 5 };
 
 constexpr int kSlots = 3;                       // pipeline depth of the host-buffer API
 constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot
@@ -252,7 +253,9 @@ int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop
 {
     int f = forced;
     if (f == kAuto) {
-        if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && !early_stop) f = kC4Thread;
+        if (method == LDPC535_METHOD_HARD && c->fits_warp && c->t.N == 64 && (c->t.M & 1) == 0 &&
+            c->t.K % 8 == 0) f = kHard64;
+        else if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && !early_stop) f = kC4Thread;
         else if (c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT) f = kRegular;
         else if (c->fits_warp) f = kWarp;
         else f = kBlock;
@@ -337,6 +340,14 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
     p.stage_tables = c->stage_tables; p.tabA_bytes = c->tabA_bytes; p.tabB_bytes = c->tabB_bytes;
     cudaError_t e;
     if (family == kRegular && dbg) family = kBlock;            // message dumps live in the generic kernel
+    if (family == kHard64) {
+        const long long warps = (p.n_win + kHardUnroll - 1) / kHardUnroll;
+        const int grid = (int)std::min<long long>((warps + kHardThreads / 32 - 1) / (kHardThreads / 32),
+                                                  (long long)c->sm_count * 8);
+        if (c->dc_t == 6) decode_hard64_kernel<6><<<grid, kHardThreads, 0, st>>>(p);
+        else decode_hard64_kernel<16><<<grid, kHardThreads, 0, st>>>(p);
+        e = cudaGetLastError();
+    } else
     if (family == kRegular) {
         // BASELINE config 4's size gets the fully unrolled instantiation
         const bool fixed8k = c->t.M == 4096 && c->t.N == 8192 && c->block_threads == 1024;
@@ -580,6 +591,7 @@ const char *ldpc535_code_kernel_name(const ldpc535_code *c, int method)
     case kBlock: return "block";
     case kC4Thread: return "c4-thread";
     case kRegular: return "regular";
+    case kHard64: return "hard64";
     default: return "unsupported";
     }
 }

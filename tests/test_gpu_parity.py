@@ -543,3 +543,23 @@ def test_pool_shards_and_gathers(c4, devices):
     for a, b in zip(pool.decode(stream, win_offset=offs, polarity=pol), c4.decode(stream, win_offset=offs, polarity=pol)):
         assert np.array_equal(a, b)
     pool.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1000, 4099])
+def test_hard_decision_kernel_vs_oracle(c4, shipped, n):
+    """Method 3 on the default dispatch (the dedicated HBM-bound kernel): aligned frames, then
+    arbitrary window offsets with both polarities."""
+    assert c4.kernel_name(3) == "hard64"
+    _, _, sym = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], n, 1.0, seed=300 + n)
+    wb, wit, wsy, _ = O.decode_frames(sym, shipped["Hp"], method=3, iterations=5, early_stop=True, threads=4)
+    b, sy, it = c4.decode(sym, method=3)
+    assert np.array_equal(b, wb) and np.array_equal(sy, wsy) and not it.any()
+    stream = sym.reshape(-1)
+    if stream.size > 64:
+        rng = np.random.default_rng(n)
+        offs = rng.integers(0, stream.size - 63, 500).astype(np.int64)
+        pol = rng.choice(np.array([-1, 1], np.int8), 500)
+        wins = np.stack([stream[o:o + 64] * q for o, q in zip(offs, pol)])
+        wb, _, wsy, _ = O.decode_frames(wins, shipped["Hp"], method=3, iterations=5, early_stop=True, threads=4)
+        b, sy, it = c4.decode(stream, method=3, win_offset=offs, polarity=pol)
+        assert np.array_equal(b, wb) and np.array_equal(sy, wsy)
