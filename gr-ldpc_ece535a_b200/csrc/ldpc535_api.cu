@@ -341,11 +341,13 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
     cudaError_t e;
     if (family == kRegular && dbg) family = kBlock;            // message dumps live in the generic kernel
     if (family == kHard64) {
-        const long long warps = (p.n_win + kHardUnroll - 1) / kHardUnroll;
+        const long long warps = (p.n_win + 31) / 32;
+        auto kern = (c->dc_t == 6) ? decode_hard64_kernel<6> : decode_hard64_kernel<16>;
+        int per_sm = 8;                    // grid = exactly the resident CTAs: one wave, no tail
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHardThreads, 0);
         const int grid = (int)std::min<long long>((warps + kHardThreads / 32 - 1) / (kHardThreads / 32),
-                                                  (long long)c->sm_count * 8);
-        if (c->dc_t == 6) decode_hard64_kernel<6><<<grid, kHardThreads, 0, st>>>(p);
-        else decode_hard64_kernel<16><<<grid, kHardThreads, 0, st>>>(p);
+                                                  (long long)c->sm_count * std::max(per_sm, 1));
+        kern<<<grid, kHardThreads, 0, st>>>(p);
         e = cudaGetLastError();
     } else
     if (family == kRegular) {
