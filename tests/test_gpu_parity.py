@@ -563,3 +563,55 @@ def test_hard_decision_kernel_vs_oracle(c4, shipped, n):
         wb, _, wsy, _ = O.decode_frames(wins, shipped["Hp"], method=3, iterations=5, early_stop=True, threads=4)
         b, sy, it = c4.decode(stream, method=3, win_offset=offs, polarity=pol)
         assert np.array_equal(b, wb) and np.array_equal(sy, wsy)
+
+
+def _dense_code(M, N, col_deg, seed):
+    """Random H = [A | B] with A invertible-by-column-pivoting and dense columns (exercises the
+    <16, 8> kernel instantiations and bit-flip decisions that really flip)."""
+    rng = np.random.default_rng(seed)
+    for _ in range(200):
+        H = np.zeros((M, N), np.int32)
+        for c in range(N):
+            rows = rng.choice(M, size=min(M, col_deg[c % len(col_deg)]), replace=False)
+            H[rows, c] = 1
+        if H.sum(1).max() > 16 or H.sum(1).min() < 2:
+            continue
+        try:
+            L.Code(H, device=-1)
+            return H
+        except L.Ldpc535Error:
+            continue
+    raise RuntimeError("no invertible dense code found")
+
+
+@pytest.mark.parametrize("M,N,col_deg", [(8, 16, (5, 3, 4, 6)), (16, 32, (3, 5, 2, 4, 7)), (24, 48, (3, 2, 4, 5)),
+                                         (32, 64, (3, 2, 4, 8))])
+def test_dense_small_codes_all_methods(M, N, col_deg):
+    """Rate-1/2 codes (the reference's L/U layout needs N = 2M) denser than it ships: check degree up to 16, bit degree up to 8, a bit
+    degree above M/2 so that decodeBitFlipping (:439-473) actually flips.  Every method vs the
+    oracle, warp and CTA kernels."""
+    H = _dense_code(M, N, col_deg, seed=M * 100 + N)
+    Hp, Lm, Um, _ = O.reorder_h(H)
+    code = L.Code(H, device=0)
+    assert (code.M, code.N) == (M, N)
+    _, cw, sym = util.synth_frames(Hp, Lm, Um, 400, 5.0, seed=M)
+    enc = code.encode(util.pack_bits_msb(cw[:, M:]))
+    assert np.array_equal(sym_to_bits(enc).reshape(400, N), cw)
+    flips = 0
+    for kern in ("warp", "block"):
+        code.set_kernel(kern)
+        for method in (1, 0, 2, 3):
+            for iters in (5, 12):
+                wb, wit, wsy, _ = O.decode_frames(sym, Hp, method=method, iterations=iters, early_stop=True,
+                                                  threads=4)
+                b, sy, it = code.decode(sym, method=method, max_iters=iters)
+                assert np.array_equal(b, wb), (kern, method, iters)
+                assert np.array_equal(sy, wsy), (kern, method, iters)
+                if method in (0, 1):
+                    assert np.array_equal(it, wit), (kern, method, iters)
+        hb, _, _ = code.decode(sym, method=3)
+        fb, _, _ = code.decode(sym, method=2)
+        flips += int((hb != fb).any(axis=1).sum())
+    if max(col_deg) > M // 2:
+        assert flips > 0, "bit-flip never flipped: the test does not exercise :464-465"
+    code.close()
