@@ -253,8 +253,11 @@ int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop
 {
     int f = forced;
     if (f == kAuto) {
-        if (method == LDPC535_METHOD_HARD && c->fits_warp && c->t.N == 64 && (c->t.M & 1) == 0 &&
-            c->t.K % 8 == 0) f = kHard64;
+        // bit-flip flips a bit only when MORE than M/2 of its checks disagree (reference :464): with
+        // every bit degree <= M/2 it can never flip and equals the hard decision
+        const bool flipless = method == LDPC535_METHOD_BITFLIP && c->t.dv_max <= c->t.M / 2;
+        if ((method == LDPC535_METHOD_HARD || flipless) && c->fits_warp && c->t.N == 64 &&
+            (c->t.M & 1) == 0 && c->t.K % 8 == 0) f = kHard64;
         else if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && !early_stop) f = kC4Thread;
         else if (c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT) f = kRegular;
         else if (c->fits_warp) f = kWarp;

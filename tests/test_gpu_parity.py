@@ -550,10 +550,14 @@ def test_hard_decision_kernel_vs_oracle(c4, shipped, n):
     """Method 3 on the default dispatch (the dedicated HBM-bound kernel): aligned frames, then
     arbitrary window offsets with both polarities."""
     assert c4.kernel_name(3) == "hard64"
+    assert c4.kernel_name(2) == "hard64"          # no bit of the shipped code can flip (degree <= M/2)
+    fb, fs, _ = c4.decode(util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], n, 1.0, seed=300 + n)[2], method=2)
     _, _, sym = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], n, 1.0, seed=300 + n)
     wb, wit, wsy, _ = O.decode_frames(sym, shipped["Hp"], method=3, iterations=5, early_stop=True, threads=4)
     b, sy, it = c4.decode(sym, method=3)
     assert np.array_equal(b, wb) and np.array_equal(sy, wsy) and not it.any()
+    w2, _, s2, _ = O.decode_frames(sym, shipped["Hp"], method=2, iterations=5, early_stop=True, threads=4)
+    assert np.array_equal(fb, w2) and np.array_equal(fs, s2)
     stream = sym.reshape(-1)
     if stream.size > 64:
         rng = np.random.default_rng(n)
