@@ -41,7 +41,7 @@ def synth(code, n, ebn0, sp, gen):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="decode_c4,decode_warp,decode_block,encode_small,encode_generic")
+    ap.add_argument("--which", default="decode_c4,decode_warp,methods,decode_block,encode_small,encode_generic")
     ap.add_argument("--c4-codewords", type=int, default=2_000_000)
     ap.add_argument("--c8k-codewords", type=int, default=20_000)
     args = ap.parse_args()
