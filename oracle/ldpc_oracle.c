@@ -5,13 +5,20 @@
  * this file: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
  * `--impl reference` legs may use it, and only as the checker / the CPU number.
  *
- * Parity pinning: the reference (GNU Radio 3.7 + Boost uBLAS + LAPACKE) cannot be
- * built in this image, so there is no oracle/_ref.  This restatement is pinned
- * against the ONLY golden vectors the reference holds for the path: the two QA
- * known-answer tests on the 8x16 code (python/qa_ldpc_encoder_bc.py:23-46,
- * python/qa_ldpc_decoder_cb.py:20-43; tests/test_oracle_kat.py).  For the shipped
- * 32x64 code and anything larger the reference's own tests pin nothing
- * ("parity unpinned" beyond the 8x16 KATs); goldens there come from this file.
+ * Parity pinning, two anchors:
+ *  (1) the ONLY golden vectors the reference holds for the path: the two QA known-answer
+ *      tests on the 8x16 code (python/qa_ldpc_encoder_bc.py:23-46,
+ *      python/qa_ldpc_decoder_cb.py:20-43; tests/test_oracle_kat.py);
+ *  (2) the reference's OWN CODE run here: oracle/_ref/libldpc_ref.so is the reference's
+ *      lib/ldpc_decoder_cb_impl.cc + lib/ldpc_encoder_bc_impl.cc compiled unmodified from
+ *      /root/reference against small stand-ins for their dependencies (oracle/refshim/: uBLAS
+ *      containers, gr::block base class, LAPACKE_dgesv -- GNU Radio 3.7, Boost and LAPACK are
+ *      not in this image; oracle/ref_driver.cc, oracle/Makefile).  tests/test_reference_build.py
+ *      checks every function of this file against it -- tables, parity, all four decode
+ *      methods on all five reference matrices, both general_work bodies call by call with the
+ *      sync machine -- live and through tests/golden/ref_build_golden.npz (outputs of that
+ *      library, tools/gen_ref_golden.py).  What the stand-ins cannot pin: the real uBLAS /
+ *      LAPACK binaries (see DESIGN.md "Oracle" for why they cannot change the values).
  *
  * Every function follows the reference loop for loop (dense H scans, fp64,
  * ascending accumulation order, per-call allocation of the message matrices)

@@ -1,4 +1,5 @@
-"""CPU: bench.py's reference arm (the oracle on host cores) prints the contract's JSON line."""
+"""CPU: bench.py's reference arm (oracle/_ref -- the reference's own decoder sources -- on host
+cores, or the oracle port where that library is not built) prints the contract's JSON line."""
 import json
 import os
 import subprocess
@@ -14,7 +15,11 @@ def test_reference_arm_json_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "Gbit/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["steps"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref as R
+    assert line["cpu_baseline"]["kind"] == ("reference" if R.available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
+    if R.available():                       # the same-work figure of the port is reported beside it
+        assert 0 < line["cpu_baseline"]["port_same_work"]["value"] <= line["value"] * 1.5
     assert line["e2e"] == {"value": line["value"], "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
 
