@@ -180,4 +180,146 @@ decode_regular_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-table variant (compile-time sizes only): the kernel BASELINE config 4's code runs on.
+// Same arithmetic, same message layout, but the per-bit state that never changes during a launch
+// lives in REGISTERS instead of shared memory: 512 threads (<= 128 registers each), a thread owns
+// NF/512 bits and MF/512 checks for the whole launch and keeps the packed address row of each of
+// its bits (loaded once per CTA) and the bit's intrinsic value r (loaded once per codeword) in
+// registers.  Per iteration and bit this drops the LDS.64 of the table row, its unpacking and the
+// LDS of r: 27.2 -> 23.2 instructions and 7.5 -> 6.5 shared-memory wavefronts per edge-iteration,
+// and fewer entries in the MIO queue that LDS/STS share with MUFU (the top stall of the
+// 1024-thread kernel).  Measured on B200: 8.17e11 -> 8.96e11 edge-iterations/s at fixed
+// iterations.  What was tried on top and rejected is in profiles/r1_microbench.txt (two codewords
+// per CTA half an iteration apart, explicit load/compute/store batching, 256 and 1024 threads,
+// r or the table back in shared memory).
+// Shared memory: msg[DC*M] | hard[N/32] | red.
+template <int DC, int MF, int NF>
+__host__ __device__ constexpr size_t regular_rt_smem_bytes()
+{
+    return 4 * (size_t)DC * MF + 4 * (size_t)(NF / 32) + 16;
+}
+
+template <int DC, int DV, int MF, int NF>
+__global__ void __launch_bounds__(512, 1)
+decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row4)
+{
+    static_assert(DV == 3, "three message addresses per bit");
+    static_assert(MF % 512 == 0 && NF % 512 == 0, "fixed sizes are whole multiples of the CTA");
+    constexpr int NT = 512, CQ = MF / NT, BQ = NF / NT, M = MF, N = NF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *msg = reinterpret_cast<float *>(smem_raw);
+    uint32_t *hard = reinterpret_cast<uint32_t *>(msg + (size_t)DC * M);
+    int *red = reinterpret_cast<int *>(hard + N / 32);
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    // the address rows of this thread's bits: once per CTA, coalesced 8-byte loads
+    uint2 vt[BQ];
+#pragma unroll
+    for (int q = 0; q < BQ; q++) vt[q] = __ldg(reinterpret_cast<const uint2 *>(var_row4) + q * NT + tid);
+
+    const bool tag = p.early_stop != 0;
+    const uint32_t tagmask = tag ? 0x40000000u : 0u;
+    for (long long w = blockIdx.x; w < p.n_win; w += gridDim.x) {
+        const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
+        const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
+        const bool ok = off >= 0 && off + N <= p.n_sym;
+        float r[BQ];
+#pragma unroll
+        for (int q = 0; q < BQ; q++) r[q] = ok ? (-pol * kSpaScale) * load_re(p, off + q * NT + tid) : 0.f;
+        // pull the next window of this CTA towards L2 while this one iterates (one 128-byte line per thread)
+        if (w + gridDim.x < p.n_win) {
+            const long long offn = p.win_offset ? p.win_offset[w + gridDim.x] : (w + gridDim.x) * (long long)N;
+            if (offn >= 0 && offn + N <= p.n_sym) {
+                const char *base = p.sym_re ? reinterpret_cast<const char *>(p.sym_re + offn)
+                                            : reinterpret_cast<const char *>(p.sym + offn);
+                const int bytes = p.sym_re ? 4 * N : 8 * N;
+                if (tid * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + tid * 128));
+            }
+        }
+        __syncthreads();                                   // previous window fully drained
+        if (tid == 0) red[0] = 0;
+        // M_ji = r_i on every edge, stored as t = copysign(2^-|M|, M), no tags yet
+#pragma unroll
+        for (int q = 0; q < BQ; q++) {
+            const float t = to_check_msg(r[q]);
+            msg[vt[q].x & 0xffffu] = t;
+            msg[vt[q].x >> 16] = t;
+            msg[vt[q].y & 0xffffu] = t;
+        }
+        __syncthreads();
+
+        int iters = p.max_iters;
+        bool clean = false;
+        for (int h = 0; h < p.max_iters; h++) {
+            // ---- check nodes (+ parity of the previous iteration's decisions from the tags) ----
+            uint32_t tagbad = 0;
+#pragma unroll
+            for (int q = 0; q < CQ; q++) {
+                const int j = q * NT + tid;
+                float m[DC];
+#pragma unroll
+                for (int s = 0; s < DC; s++) m[s] = msg[s * M + j];
+                tagbad |= check_node_spa<DC, true>(m);
+#pragma unroll
+                for (int s = 0; s < DC; s++) msg[s * M + j] = m[s];
+            }
+            if (tag) {
+                const int bad = __syncthreads_or((int)(tagbad & 0x40000000u));
+                if (h > 0 && !bad) { iters = h; clean = true; break; }
+            } else {
+                __syncthreads();
+            }
+            // ---- variable nodes: L, hard decision, next messages (tagged with the decision) ----
+#pragma unroll
+            for (int q = 0; q < BQ; q++) {
+                const int i0 = (int)(vt[q].x & 0xffffu), i1 = (int)(vt[q].x >> 16), i2 = (int)(vt[q].y & 0xffffu);
+                float x[DV] = {msg[i0], msg[i1], msg[i2]};
+                const float L = var_node_spa<DV>(x, DV, r[q]);
+                const bool b = (L <= 0.f);
+                const uint32_t tagbit = b ? tagmask : 0u;
+                msg[i0] = __uint_as_float(__float_as_uint(to_check_msg(x[0])) | tagbit);
+                msg[i1] = __uint_as_float(__float_as_uint(to_check_msg(x[1])) | tagbit);
+                msg[i2] = __uint_as_float(__float_as_uint(to_check_msg(x[2])) | tagbit);
+                const uint32_t wd = __ballot_sync(0xffffffffu, b);
+                if (lane == 0) hard[(q * NT + tid) >> 5] = wd;
+            }
+            __syncthreads();
+        }
+
+        // ---- saturating syndrome weight of the final decision (checkFrame, :236-253) ----
+        int cnt = 0;
+        if (!clean) {
+            for (int j = tid; j < M; j += NT) {
+                uint32_t pj = 0;
+#pragma unroll
+                for (int s = 0; s < DC; s++) {
+                    const int v = __ldg(p.chk_var + s * M + j);
+                    pj ^= hard[v >> 5] >> (v & 31);
+                }
+                cnt += (int)(pj & 1u);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0 && cnt) atomicAdd(&red[0], cnt);
+            __syncthreads();
+            cnt = red[0];
+        }
+        // ---- outputs: data bits M .. N-1, MSB first (:207-219) ----
+        for (int b = tid; b < p.nbytes; b += NT) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int v = M + 8 * b + q;
+                if (v < N) bits |= ((hard[v >> 5] >> (v & 31)) & 1u) << q;
+            }
+            p.out_bytes[w * p.nbytes + b] = ok ? pack_msb_first(bits) : (uint8_t)0;
+        }
+        if (tid == 0) {
+            if (p.out_synd) p.out_synd[w] = ok ? (uint8_t)min(cnt, p.thr + 1) : (uint8_t)255;
+            if (p.out_iters) p.out_iters[w] = ok ? (uint8_t)min(iters, 255) : (uint8_t)255;
+        }
+    }
+}
+
 }  // namespace ldpc535

@@ -74,6 +74,7 @@ struct ldpc535_code {
     int32_t *d_w_pos_edge = nullptr;
     uint16_t *d_var_row4 = nullptr;   // [N][4] message addresses of a bit (regular codes, dv <= 4)
     bool fits_regular = false;
+    int regular_variant = 1;          // 1: 512-thread register-table kernel (fixed sizes), 0: 1024-thread kernel
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
     int tabA_bytes = 0, tabB_bytes = 0;
     int dc_t = 0, dv_t = 0;           // template sizes used (6/3 or 16/8), 0 = unsupported degrees
@@ -209,6 +210,7 @@ int finish_create(ldpc535_code *c)
     int nt = std::max(t.M, (t.N + 1) / 2);
     nt = std::min(1024, ((nt + 31) / 32) * 32);
     c->block_threads = std::max(nt, 64);
+    if (const char *e = getenv("LDPC535_REGULAR_VARIANT")) c->regular_variant = atoi(e) ? 1 : 0;
     if (const char *e = getenv("LDPC535_BLOCK_THREADS")) c->block_threads = std::max(64, std::min(1024, atoi(e) / 32 * 32));
     if (!c->fits_warp && !c->fits_block)
         return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the shared-memory resident decoder");
@@ -361,14 +363,27 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
     } else
     if (family == kRegular) {
         // BASELINE config 4's size gets the fully unrolled instantiation
+        // BASELINE config 4's size gets the compile-time-size instantiations: by default the
+        // register-table kernel (512 threads); LDPC535_REGULAR_VARIANT=0 selects the 1024-thread
+        // kernel with the tables in shared memory (kept for A/B measurements and other sizes)
         const bool fixed8k = c->t.M == 4096 && c->t.N == 8192 && c->block_threads == 1024;
-        auto kern = fixed8k ? decode_regular_kernel<6, 3, 4096, 8192> : decode_regular_kernel<6, 3>;
-        const size_t smem = regular_smem_bytes(6, c->t.M, c->t.N);
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) {
-            const int grid = (int)std::min<long long>(p.n_win, (long long)c->sm_count);
-            kern<<<grid, c->block_threads, smem, st>>>(p, c->d_var_row4);
-            e = cudaGetLastError();
+        const int grid = (int)std::min<long long>(p.n_win, (long long)c->sm_count);
+        if (fixed8k && c->regular_variant == 1) {
+            auto kern = decode_regular_rt_kernel<6, 3, 4096, 8192>;
+            const size_t smem = regular_rt_smem_bytes<6, 4096, 8192>();
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) {
+                kern<<<grid, 512, smem, st>>>(p, c->d_var_row4);
+                e = cudaGetLastError();
+            }
+        } else {
+            auto kern = fixed8k ? decode_regular_kernel<6, 3, 4096, 8192> : decode_regular_kernel<6, 3>;
+            const size_t smem = regular_smem_bytes(6, c->t.M, c->t.N);
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) {
+                kern<<<grid, c->block_threads, smem, st>>>(p, c->d_var_row4);
+                e = cudaGetLastError();
+            }
         }
     } else if (family == kC4Thread) e = launch_c4_thread(p, dbg, c->sm_count, st);
     else if (c->dc_t == 6) e = launch_generic<6, 3>(c, family, method, dbg, p, st);

@@ -420,6 +420,39 @@ def test_c8k_kernels_agree(c8k):
             assert np.array_equal(x, y)
 
 
+def test_c8k_regular_kernel_variants_agree(c8k, monkeypatch):
+    """The 512-thread register-table kernel (default for this size) and the 1024-thread kernel with
+    the tables in shared memory (LDPC535_REGULAR_VARIANT=0): identical bytes, syndrome weights and
+    iteration counts, for batch sizes around the grid size, with search windows and polarity."""
+    monkeypatch.setenv("LDPC535_REGULAR_VARIANT", "0")
+    other = L.Code(c8k.h_csr() + (c8k.M, c8k.N), device=0)
+    monkeypatch.delenv("LDPC535_REGULAR_VARIANT")
+    assert c8k.kernel_name() == "regular" and other.kernel_name() == "regular"
+    rng = np.random.default_rng(17)
+    n = 300
+    data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
+    noisy = c8k.encode(data)
+    assert np.array_equal(noisy, other.encode(data))
+    noisy.real += rng.standard_normal(noisy.shape, dtype=np.float32) * np.float32(0.8)
+    for cnt in (1, 2, 147, 148, 149, 300):
+        for mi, es in ((50, True), (7, False)):
+            a = c8k.decode(noisy[:cnt], method=1, max_iters=mi, early_stop=es)
+            b = other.decode(noisy[:cnt], method=1, max_iters=mi, early_stop=es)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (cnt, mi, es)
+    # windows at arbitrary offsets with both polarities
+    flat = noisy[:4].reshape(-1)
+    offs = np.array([0, 8192, 5, 3 * 8192, 3 * 8192 - 1, 2 * 8192 - 7], np.int64)
+    pol = np.array([1, -1, 1, -1, 1, -1], np.int8)
+    a = c8k.decode(flat, method=1, max_iters=10, early_stop=True, win_offset=offs, polarity=pol)
+    b = other.decode(flat, method=1, max_iters=10, early_stop=True, win_offset=offs, polarity=pol)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    with pytest.raises(L.Ldpc535Error):          # a window past the end is refused by the host API
+        c8k.decode(flat, method=1, win_offset=np.array([3 * 8192 + 1], np.int64))
+    other.close()
+
+
 def test_c8k_messages_within_tolerance(c8k):
     rng = np.random.default_rng(14)
     data = rng.integers(0, 256, (2, c8k.nbytes)).astype(np.uint8)
