@@ -1,0 +1,188 @@
+// Large-code encoder: parity c = P d over GF(2) by table look-up (the "Method of the Four
+// Russians" applied to the generator), for codes whose dense P no longer fits a per-frame
+// AND/XOR scan (BASELINE config 4's n = 8192 code: P is 4096 x 4096 bits = 2 MB, 524 288
+// AND-XOR words per frame, which capped encode_generic_kernel at ~36 % of the HBM write
+// roofline on the integer pipe).
+//
+// One input BYTE selects 8 columns of P at once.  For every byte position g (K/8 of them) and
+// byte value v a table row holds the XOR of the selected columns, cut into blocks of 1024 parity
+// rows:  T[rb][g][v] = 128 bytes.  A frame's parity block is the XOR of K/8 table rows -- 8x
+// fewer word operations than the scan, all of them 128-bit.  The table (M/1024 * K/8 * 32 KB =
+// 64 MB for the n = 8192 code) lives in HBM/L2 and is built once per code on the GPU
+// (encode_m4r_build_kernel).
+//
+// encode_m4r_kernel: a CTA of 1024 threads encodes a tile of 128 * TPF frames.  For each row
+// block the CTA streams the K/8 tables T[rb][g][*] (32 KB each) through a ring of shared-memory
+// stages with cp.async; 8 lanes share a frame, lane c owns the 16-byte chunk c of the running
+// XOR, so every shared-memory wavefront is one whole table row (conflict-free), and each table
+// byte fetched from L2 is used by all frames of the tile.  The bit order inside a table row is
+// chosen so that the 8 lanes of a frame write 128 contiguous bytes of BPSK symbols per store:
+//     chunk c, word i, bit b   <->   parity row  rb*1024 + 16*(16 i + b/2) + 2 c + (b & 1).
+// The data half of the codeword (symbols M .. N-1) is written by the same kernel, spread over its steps.
+// Output-bandwidth bound by design: 8 N bytes out per frame; what limits it in practice is the
+// shared-memory read of 128 bytes per (frame, byte position, row block).
+#pragma once
+#include "encode_kernels.cuh"
+
+namespace ldpc535 {
+
+constexpr int kM4rRows = 1024;          // parity rows per block  (128-byte table rows)
+constexpr int kM4rThreads = 1024;
+constexpr int kM4rSlots = kM4rThreads / 8;
+constexpr int kM4rStages = 4;           // 4 x 32 KB ring
+constexpr size_t kM4rStageBytes = 256 * 128;
+
+__host__ __device__ inline size_t encode_m4r_table_bytes(int M, int K)
+{
+    return (size_t)(M / kM4rRows) * (size_t)(K / 8) * kM4rStageBytes;
+}
+
+// One warp per (row block, byte position): lane = word (c, i) of the 128-byte row.
+__global__ void __launch_bounds__(32)
+encode_m4r_build_kernel(const uint32_t *__restrict__ Pt, uint32_t *__restrict__ T, int M, int K, int mwords)
+{
+    const int G = K / 8;
+    const int rb = blockIdx.x / G, g = blockIdx.x % G;
+    const int wd = threadIdx.x, c = wd >> 2, i = wd & 3;
+    (void)M;
+    uint32_t pcol[8];                                   // permuted column words of data bits 8g .. 8g+7
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t *col = Pt + (size_t)(8 * g + j) * mwords;
+        uint32_t w = 0;
+        for (int b = 0; b < 32; b++) {
+            const int r = rb * kM4rRows + 16 * (16 * i + (b >> 1)) + 2 * c + (b & 1);
+            w |= ((__ldg(col + (r >> 5)) >> (r & 31)) & 1u) << b;
+        }
+        pcol[j] = w;
+    }
+    uint32_t *dst = T + ((size_t)blockIdx.x * 256) * 32 + wd;
+    for (int v = 0; v < 256; v++) {
+        uint32_t e = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++)                     // data bit 8g + j is bit 7-j of the byte (MSB first)
+            e ^= pcol[j] & (0u - ((v >> (7 - j)) & 1u));
+        dst[(size_t)v * 32] = e;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
+
+__device__ __forceinline__ float bpsk_bit(uint32_t word, int b)
+{
+    return __uint_as_float(0xbf800000u ^ (((word >> b) & 1u) << 31));     // 1 -> +1.0, 0 -> -1.0
+}
+
+// TPF frames per thread slot: a tile is 128 * TPF frames; the unit of work is (tile, row block), so
+// a CTA's accumulators are 128 bytes per frame and the units spread evenly over the SMs.  A unit
+// also writes its share of the data half of the codeword (K/8 / RB input bytes per frame: one
+// 4-byte word = 256 bytes of symbols every 4 RB-th step), so its stores are spread over its steps.
+// Stages are consumed two per barrier.  All per-frame addresses are 32-bit offsets from the
+// kernel's base pointers (the host splits batches so that they fit).
+// Requires K % 32 == 0, M % 1024 == 0, (K/32) % (M/1024) == 0, p.in 4-byte aligned, p.out
+// 16-byte aligned, n_frames * K/8 < 2^32 and n_frames * N / 2 < 2^32.
+template <int TPF>
+__global__ void __launch_bounds__(kM4rThreads, 1)
+encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
+{
+    extern __shared__ __align__(128) unsigned char m4r_smem[];
+    const int tid = threadIdx.x, slot = tid >> 3, c = tid & 7;
+    const int G = p.K >> 3, RB = p.M / kM4rRows;
+    const uint32_t sys_words = (uint32_t)(G / RB) >> 2;     // 4-byte data words of a frame this unit writes out
+    const uint32_t tile_frames = (uint32_t)kM4rSlots * TPF;
+    const uint32_t n_frames = (uint32_t)p.n_frames;
+    const uint32_t n_tiles = (n_frames + tile_frames - 1) / tile_frames;
+    const uint32_t n_units = n_tiles * (uint32_t)RB;
+    const uint32_t in_wstride = (uint32_t)p.nbytes >> 2;    // input words per frame
+    const uint32_t out_qstride = (uint32_t)p.N >> 1;        // float4 (symbol pairs) per frame
+    const uint32_t *__restrict__ inw = reinterpret_cast<const uint32_t *>(p.in);
+    float4 *__restrict__ outq = reinterpret_cast<float4 *>(p.out);
+    constexpr int kV4 = (int)(kM4rStageBytes / 16);         // uint4 per stage
+    const uint4 *ring = reinterpret_cast<const uint4 *>(m4r_smem) + c;
+
+    for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const uint32_t tile = unit / (uint32_t)RB;
+        const uint32_t rb = unit - tile * (uint32_t)RB;
+        const uint32_t f0 = tile * tile_frames + slot;      // frame of t = 0; frame t is f0 + 128 t
+        const uint32_t in0 = f0 * in_wstride;               // word offset of frame f0
+        const uint32_t out0 = f0 * out_qstride;             // float4 offset of frame f0
+        const int tmax = f0 >= n_frames ? 0 : (int)min((uint32_t)TPF, (n_frames - f0 + kM4rSlots - 1) / kM4rSlots);
+        const uint4 *Trb = T + (size_t)rb * G * kV4 + tid;
+        auto load_stage = [&](int g) {                      // T[rb][g][*] -> ring slot g % kM4rStages
+            if (g < G) {
+                const uint4 *src = Trb + (size_t)g * kV4;
+                uint4 *dst = reinterpret_cast<uint4 *>(m4r_smem + (size_t)(g & (kM4rStages - 1)) * kM4rStageBytes) + tid;
+                cp_async16(dst, src);
+                cp_async16(dst + kM4rThreads, src + kM4rThreads);
+            }
+        };
+        __syncthreads();                                    // the previous unit's last stages have been read
+        load_stage(0); load_stage(1); cp_async_commit();
+        uint4 acc[TPF];
+#pragma unroll
+        for (int t = 0; t < TPF; t++) acc[t] = make_uint4(0u, 0u, 0u, 0u);
+        for (int g4 = 0; g4 < G; g4 += 4) {
+            uint32_t vw[TPF];                               // input bytes g4 .. g4+3 of this slot's frames
+#pragma unroll
+            for (int t = 0; t < TPF; t++)
+                vw[t] = (t < tmax) ? __ldg(inw + (in0 + (uint32_t)t * kM4rSlots * in_wstride + ((uint32_t)g4 >> 2))) : 0u;
+            if (((uint32_t)g4 >> 2) % (uint32_t)RB == 0) {
+                // data half: word sw of the frame = 32 symbols = 16 float4; lane c writes float4 c and c + 8
+                const uint32_t sw = rb * sys_words + ((uint32_t)g4 >> 2) / (uint32_t)RB;
+#pragma unroll
+                for (int t = 0; t < TPF; t++) {
+                    if (t < tmax) {
+                        const uint32_t w = __ldg(inw + (in0 + (uint32_t)t * kM4rSlots * in_wstride + sw));
+                        float4 *dst = outq + (out0 + (uint32_t)t * kM4rSlots * out_qstride + ((uint32_t)p.M >> 1) + 16u * sw + c);
+                        // symbol j of the word is bit 8 (j / 8) + 7 - j % 8 (bytes in order, MSB first)
+                        const int b0 = 8 * (c >> 2) + 7 - 2 * (c & 3);
+                        __stcs(dst, make_float4(bpsk_bit(w, b0), 0.f, bpsk_bit(w, b0 - 1), 0.f));
+                        __stcs(dst + 8, make_float4(bpsk_bit(w, b0 + 16), 0.f, bpsk_bit(w, b0 + 15), 0.f));
+                    }
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int g = g4 + 2 * half;
+                cp_async_wait<0>();                         // stages g, g+1 (issued one barrier ago) have landed for this thread ...
+                __syncthreads();                            // ... and for everyone; the ring slots of g-2, g-1 are free
+                load_stage(g + 2);
+                load_stage(g + 3);
+                cp_async_commit();
+#pragma unroll
+                for (int gg = 0; gg < 2; gg++) {
+                    const uint4 *stage = ring + (size_t)((2 * half + gg) & (kM4rStages - 1)) * kV4;   // (g + gg) % 4, g4 % 4 == 0
+#pragma unroll
+                    for (int t = 0; t < TPF; t++) {
+                        const uint32_t v = (vw[t] >> (8 * (2 * half + gg))) & 0xffu;
+                        const uint4 e = stage[v * 8];
+                        acc[t].x ^= e.x; acc[t].y ^= e.y; acc[t].z ^= e.z; acc[t].w ^= e.w;
+                    }
+                }
+            }
+        }
+        // parity symbols of this row block: 8 lanes of a frame write 128 contiguous bytes per store
+#pragma unroll
+        for (int t = 0; t < TPF; t++) {
+            if (t >= tmax) continue;
+            float4 *dst = outq + (out0 + (uint32_t)t * kM4rSlots * out_qstride + rb * (kM4rRows / 2) + c);
+            const uint32_t w4[4] = {acc[t].x, acc[t].y, acc[t].z, acc[t].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int s2 = 0; s2 < 16; s2++)
+                    __stcs(dst + 8 * (16 * i + s2),
+                           make_float4(bpsk_bit(w4[i], 2 * s2), 0.f, bpsk_bit(w4[i], 2 * s2 + 1), 0.f));
+        }
+        cp_async_wait<0>();
+    }
+}
+
+}  // namespace ldpc535

@@ -21,6 +21,7 @@
 #include "decode_regular_kernel.cuh"
 #include "decode_hard_kernel.cuh"
 #include "encode_kernels.cuh"
+#include "encode_m4r_kernel.cuh"
 #include "host_pack.h"
 #include "ldpc535_default_code.h"
 
@@ -76,6 +77,8 @@ struct ldpc535_code {
     bool fits_regular = false;
     int regular_variant = 1;          // 1: 512-thread register-table kernel (fixed sizes), 0: 1024-thread kernel
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
+    uint32_t *d_m4r = nullptr;        // table of the look-up encoder (large codes), see encode_m4r_kernel.cuh
+    bool use_m4r = true;              // LDPC535_ENCODER=generic switches it off (A/B measurements)
     int tabA_bytes = 0, tabB_bytes = 0;
     int dc_t = 0, dv_t = 0;           // template sizes used (6/3 or 16/8), 0 = unsupported degrees
     bool fits_warp = false, fits_block = false, is_c4 = false;
@@ -174,6 +177,17 @@ int finish_create(ldpc535_code *c)
         if ((st = upload(&c->d_Pw, Pw.data(), Pw.size() * 4, Pw.size() * 4))) return st;
     }
 
+    // large codes: the look-up encoder's table, built on the device from the column masks
+    if (const char *e = getenv("LDPC535_ENCODER")) c->use_m4r = strcmp(e, "generic") != 0;
+    if (t.M % kM4rRows == 0 && t.K % 32 == 0 && t.M >= kM4rRows && (t.K / 32) % (t.M / kM4rRows) == 0 &&
+        encode_m4r_table_bytes(t.M, t.K) <= ((size_t)512 << 20) &&
+        (size_t)kM4rStages * kM4rStageBytes <= c->smem_optin) {
+        CU(cudaMalloc(reinterpret_cast<void **>(&c->d_m4r), encode_m4r_table_bytes(t.M, t.K)));
+        encode_m4r_build_kernel<<<(t.M / kM4rRows) * (t.K / 8), 32>>>(c->d_Pt, c->d_m4r, t.M, t.K, t.mwords);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+    }
+
     // regular code -> the specialised CTA-per-codeword kernel
     {
         bool regular = t.dv_max <= 4;
@@ -233,7 +247,7 @@ void release(ldpc535_code *c)
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
-    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_var_row4); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
     delete c;
 }
 
@@ -405,6 +419,29 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
         const long long warps = ((long long)n_frames + 31) / 32;
         const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)c->sm_count * 8);
         encode_small_kernel<<<grid, 256, 0, st>>>(p);
+    } else if (c->d_m4r && c->use_m4r && n_frames >= 256 && (reinterpret_cast<uintptr_t>(d_in) & 3) == 0 &&
+               (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+        // look-up encoder; batches are cut so that the kernel's 32-bit frame offsets hold
+        const long long sms = c->sm_count, rbs = t.M / kM4rRows;
+        const long long chunk_max = std::max<long long>(1024, ((1ll << 32) / std::max(t.N / 2, p.nbytes / 4) - 1) / 1024 * 1024);
+        for (long long done = 0; done < (long long)n_frames; done += chunk_max) {
+            const long long nf = std::min<long long>(chunk_max, (long long)n_frames - done);
+            EncodeParams q = p;
+            q.in = p.in + done * p.nbytes; q.out = p.out + done * t.N; q.n_frames = nf;
+            // frames per tile chosen so that every SM has units when the batch allows
+            auto units_of = [&](int f) { return ((nf + (long long)kM4rSlots * f - 1) / ((long long)kM4rSlots * f)) * rbs; };
+            const int tpf = units_of(8) >= 2 * sms ? 8 : units_of(4) >= 2 * sms ? 4 : units_of(2) >= sms ? 2 : 1;
+            void (*kern)(const EncodeParams, const uint4 *) =
+                tpf == 8 ? encode_m4r_kernel<8> : tpf == 4 ? encode_m4r_kernel<4> : tpf == 2 ? encode_m4r_kernel<2> : encode_m4r_kernel<1>;
+            const size_t smem = (size_t)kM4rStages * kM4rStageBytes;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
+            kern<<<(int)std::min<long long>(units_of(tpf), sms), kM4rThreads, smem, st>>>(q, reinterpret_cast<const uint4 *>(c->d_m4r));
+            if (done + chunk_max < (long long)n_frames) {
+                if ((e = cudaGetLastError()) != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("encode launch: ") + cudaGetErrorString(e));
+                c->launches++;
+            }
+        }
     } else {
         const size_t smem = encode_generic_smem_bytes(t.kwords, t.mwords);
         if (smem > c->smem_optin) return fail(LDPC535_ERR_UNSUPPORTED, "code too large for the encoder tile");

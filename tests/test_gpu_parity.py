@@ -420,6 +420,35 @@ def test_c8k_kernels_agree(c8k):
             assert np.array_equal(x, y)
 
 
+def test_c8k_lookup_encoder_equals_scan_encoder(c8k, monkeypatch):
+    """The table look-up encoder (encode_m4r_kernel, default for this size) against the AND/XOR scan
+    (encode_generic_kernel, LDPC535_ENCODER=generic): identical symbols for ragged batch sizes on
+    every tile shape (128, 256, 512, 1024 frames per CTA), device-resident for the large ones."""
+    import torch
+    monkeypatch.setenv("LDPC535_ENCODER", "generic")
+    scan = L.Code(c8k.h_csr() + (c8k.M, c8k.N), device=0)
+    monkeypatch.delenv("LDPC535_ENCODER")
+    rng = np.random.default_rng(18)
+    for n in (1, 255, 256, 257, 1000):
+        data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
+        assert np.array_equal(c8k.encode(data), scan.encode(data)), n
+    sms = L.device_info(0)["sm_count"]
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(18)
+    for n in (sms * 32 * 2 + 37, sms * 64 * 4 + 1, sms * 64 * 8 + 129, sms * 128 * 8 + 5):
+        d = torch.randint(0, 256, (n, c8k.nbytes), dtype=torch.uint8, device="cuda", generator=gen)
+        a = torch.empty((n, c8k.N, 2), dtype=torch.float32, device="cuda")
+        b = torch.empty((n, c8k.N, 2), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        c8k.encode_dev(d.data_ptr(), n, a.data_ptr())
+        scan.encode_dev(d.data_ptr(), n, b.data_ptr())
+        c8k.sync()
+        scan.sync()
+        assert torch.equal(a, b), n
+        del a, b, d
+    scan.close()
+
+
 def test_c8k_regular_kernel_variants_agree(c8k, monkeypatch):
     """The 512-thread register-table kernel (default for this size) and the 1024-thread kernel with
     the tables in shared memory (LDPC535_REGULAR_VARIANT=0): identical bytes, syndrome weights and
