@@ -23,6 +23,7 @@
 // shared-memory read of 128 bytes per (frame, byte position, row block).
 #pragma once
 #include "encode_kernels.cuh"
+#include "decode_kernels.cuh"   // smem_u32
 
 namespace ldpc535 {
 
@@ -84,90 +85,154 @@ __device__ __forceinline__ float bpsk_bit(uint32_t word, int b)
 // a CTA's accumulators are 128 bytes per frame and the units spread evenly over the SMs.  A unit
 // also writes its share of the data half of the codeword (K/8 / RB input bytes per frame: one
 // 4-byte word = 256 bytes of symbols every 4 RB-th step), so its stores are spread over its steps.
-// Stages are consumed two per barrier.  All per-frame addresses are 32-bit offsets from the
-// kernel's base pointers (the host splits batches so that they fit).
-// Requires K % 32 == 0, M % 1024 == 0, (K/32) % (M/1024) == 0, p.in 4-byte aligned, p.out
-// 16-byte aligned, n_frames * K/8 < 2^32 and n_frames * N / 2 < 2^32.
+//
+// Data movement: the table stages T[rb][g][*] (32 KB each) arrive by 1-D TMA bulk copies issued
+// by one thread, each completing on its own mbarrier (4-slot ring, two stages consumed per CTA
+// barrier, the next two requested right after it); the frames' input bytes are staged 16 bytes
+// per frame at a time with cp.async, one chunk ahead, so that no global-load latency sits in the
+// look-up loop.  All per-frame addresses are 32-bit offsets from the kernel's base pointers (the
+// host splits batches so that they fit); shared memory is addressed with 32-bit offsets too.
+// Requires K % 128 == 0, M % 1024 == 0, (K/32) % (M/1024) == 0, p.in and p.out 16-byte aligned,
+// n_frames * K/32 < 2^32 and n_frames * N / 2 < 2^32.
+// Shared memory: ring[4][32 KB] | input chunks [2][TPF][128][16 B] | 4 mbarriers.
+template <int TPF>
+__host__ __device__ constexpr size_t encode_m4r_smem_bytes()
+{
+    return (size_t)kM4rStages * kM4rStageBytes + 2 * (size_t)TPF * kM4rSlots * 16 + 64;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
 template <int TPF>
 __global__ void __launch_bounds__(kM4rThreads, 1)
 encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
 {
     extern __shared__ __align__(128) unsigned char m4r_smem[];
+    constexpr uint32_t kStage = (uint32_t)kM4rStageBytes;
+    constexpr uint32_t kInBuf = (uint32_t)TPF * kM4rSlots * 16;
     const int tid = threadIdx.x, slot = tid >> 3, c = tid & 7;
     const int G = p.K >> 3, RB = p.M / kM4rRows;
-    const uint32_t sys_words = (uint32_t)(G / RB) >> 2;     // 4-byte data words of a frame this unit writes out
+    const uint32_t smem0 = smem_u32(m4r_smem);
+    const uint32_t ring_c = smem0 + 16u * c;                       // + stage * 32 KB + v * 128
+    const uint32_t in_s = smem0 + kM4rStages * kStage;             // + buf * kInBuf + (t * 128 + slot) * 16
+    const uint32_t bars = in_s + 2 * kInBuf;                       // 4 x 8 bytes
+    const uint32_t sys_words = (uint32_t)(G / RB) >> 2;            // 4-byte data words of a frame this unit writes out
     const uint32_t tile_frames = (uint32_t)kM4rSlots * TPF;
     const uint32_t n_frames = (uint32_t)p.n_frames;
     const uint32_t n_tiles = (n_frames + tile_frames - 1) / tile_frames;
     const uint32_t n_units = n_tiles * (uint32_t)RB;
-    const uint32_t in_wstride = (uint32_t)p.nbytes >> 2;    // input words per frame
-    const uint32_t out_qstride = (uint32_t)p.N >> 1;        // float4 (symbol pairs) per frame
+    const uint32_t in_wstride = (uint32_t)p.nbytes >> 2;           // input words per frame
+    const uint32_t out_qstride = (uint32_t)p.N >> 1;               // float4 (symbol pairs) per frame
     const uint32_t *__restrict__ inw = reinterpret_cast<const uint32_t *>(p.in);
     float4 *__restrict__ outq = reinterpret_cast<float4 *>(p.out);
-    constexpr int kV4 = (int)(kM4rStageBytes / 16);         // uint4 per stage
-    const uint4 *ring = reinterpret_cast<const uint4 *>(m4r_smem) + c;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < kM4rStages; b++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bars + 8u * b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t uses = 0;                                             // completed phases of every ring slot
 
     for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const uint32_t tile = unit / (uint32_t)RB;
         const uint32_t rb = unit - tile * (uint32_t)RB;
-        const uint32_t f0 = tile * tile_frames + slot;      // frame of t = 0; frame t is f0 + 128 t
-        const uint32_t in0 = f0 * in_wstride;               // word offset of frame f0
-        const uint32_t out0 = f0 * out_qstride;             // float4 offset of frame f0
+        const uint32_t f0 = tile * tile_frames + slot;             // frame of t = 0; frame t is f0 + 128 t
+        const uint32_t in0 = f0 * in_wstride;                      // word offset of frame f0
+        const uint32_t out0 = f0 * out_qstride;                    // float4 offset of frame f0
         const int tmax = f0 >= n_frames ? 0 : (int)min((uint32_t)TPF, (n_frames - f0 + kM4rSlots - 1) / kM4rSlots);
-        const uint4 *Trb = T + (size_t)rb * G * kV4 + tid;
-        auto load_stage = [&](int g) {                      // T[rb][g][*] -> ring slot g % kM4rStages
+        const unsigned char *Trb = reinterpret_cast<const unsigned char *>(T) + (size_t)rb * G * kStage;
+        auto request_stage = [&](int g) {                          // thread 0: T[rb][g][*] -> ring slot g % 4
             if (g < G) {
-                const uint4 *src = Trb + (size_t)g * kV4;
-                uint4 *dst = reinterpret_cast<uint4 *>(m4r_smem + (size_t)(g & (kM4rStages - 1)) * kM4rStageBytes) + tid;
-                cp_async16(dst, src);
-                cp_async16(dst + kM4rThreads, src + kM4rThreads);
+                const uint32_t bar = bars + 8u * (g & (kM4rStages - 1));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(kStage) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem0 + (uint32_t)(g & (kM4rStages - 1)) * kStage), "l"(Trb + (size_t)g * kStage),
+                                "r"(kStage), "r"(bar) : "memory");
             }
         };
-        __syncthreads();                                    // the previous unit's last stages have been read
-        load_stage(0); load_stage(1); cp_async_commit();
+        auto request_input = [&](int chunk) {                      // lane c stages 16 bytes of frame t = c
+            if (c < tmax) {
+                const uint32_t dst = in_s + (uint32_t)(chunk & 1) * kInBuf + ((uint32_t)c * kM4rSlots + slot) * 16u;
+                const uint32_t *src = inw + (in0 + (uint32_t)c * kM4rSlots * in_wstride + 4u * chunk);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+            }
+            cp_async_commit();
+        };
+        __syncthreads();                                           // the previous unit has been read to the end
+        if (tid == 0) { request_stage(0); request_stage(1); }
+        request_input(0);
         uint4 acc[TPF];
 #pragma unroll
         for (int t = 0; t < TPF; t++) acc[t] = make_uint4(0u, 0u, 0u, 0u);
         for (int g4 = 0; g4 < G; g4 += 4) {
-            uint32_t vw[TPF];                               // input bytes g4 .. g4+3 of this slot's frames
-#pragma unroll
-            for (int t = 0; t < TPF; t++)
-                vw[t] = (t < tmax) ? __ldg(inw + (in0 + (uint32_t)t * kM4rSlots * in_wstride + ((uint32_t)g4 >> 2))) : 0u;
-            if (((uint32_t)g4 >> 2) % (uint32_t)RB == 0) {
-                // data half: word sw of the frame = 32 symbols = 16 float4; lane c writes float4 c and c + 8
-                const uint32_t sw = rb * sys_words + ((uint32_t)g4 >> 2) / (uint32_t)RB;
-#pragma unroll
-                for (int t = 0; t < TPF; t++) {
-                    if (t < tmax) {
-                        const uint32_t w = __ldg(inw + (in0 + (uint32_t)t * kM4rSlots * in_wstride + sw));
-                        float4 *dst = outq + (out0 + (uint32_t)t * kM4rSlots * out_qstride + ((uint32_t)p.M >> 1) + 16u * sw + c);
-                        // symbol j of the word is bit 8 (j / 8) + 7 - j % 8 (bytes in order, MSB first)
-                        const int b0 = 8 * (c >> 2) + 7 - 2 * (c & 3);
-                        __stcs(dst, make_float4(bpsk_bit(w, b0), 0.f, bpsk_bit(w, b0 - 1), 0.f));
-                        __stcs(dst + 8, make_float4(bpsk_bit(w, b0 + 16), 0.f, bpsk_bit(w, b0 + 15), 0.f));
-                    }
-                }
-            }
+            uint32_t vw[TPF];                                      // input bytes g4 .. g4+3 of this slot's frames
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 const int g = g4 + 2 * half;
-                cp_async_wait<0>();                         // stages g, g+1 (issued one barrier ago) have landed for this thread ...
-                __syncthreads();                            // ... and for everyone; the ring slots of g-2, g-1 are free
-                load_stage(g + 2);
-                load_stage(g + 3);
-                cp_async_commit();
+                if (half == 0 && (g4 & 15) == 0) cp_async_wait<0>();   // this chunk of input bytes (requested 16 steps ago)
+                __syncthreads();                                   // ring slots of g-2, g-1 and the other input buffer are free
+                if (tid == 0) { request_stage(g + 2); request_stage(g + 3); }
+                if (half == 0) {
+                    if ((g4 & 15) == 0 && g4 + 16 < G) request_input((g4 >> 4) + 1);
+                    const uint32_t ia = in_s + (uint32_t)((g4 >> 4) & 1) * kInBuf + (uint32_t)slot * 16u + (uint32_t)(g4 & 12);
+#pragma unroll
+                    for (int t = 0; t < TPF; t++) vw[t] = lds32(ia + (uint32_t)t * kM4rSlots * 16u);
+                    if (((uint32_t)g4 >> 2) % (uint32_t)RB == 0) {
+                        // data half: word sw of the frame = 32 symbols = 16 float4; lane c writes float4 c and c + 8
+                        const uint32_t sw = rb * sys_words + ((uint32_t)g4 >> 2) / (uint32_t)RB;
+                        const int b0 = 8 * (c >> 2) + 7 - 2 * (c & 3);     // symbol j of the word is bit 8 (j / 8) + 7 - j % 8
+#pragma unroll
+                        for (int t = 0; t < TPF; t++) {
+                            if (t < tmax) {
+                                const uint32_t w = __ldg(inw + (in0 + (uint32_t)t * kM4rSlots * in_wstride + sw));
+                                float4 *dst = outq + (out0 + (uint32_t)t * kM4rSlots * out_qstride + ((uint32_t)p.M >> 1) + 16u * sw + c);
+                                __stcs(dst, make_float4(bpsk_bit(w, b0), 0.f, bpsk_bit(w, b0 - 1), 0.f));
+                                __stcs(dst + 8, make_float4(bpsk_bit(w, b0 + 16), 0.f, bpsk_bit(w, b0 + 15), 0.f));
+                            }
+                        }
+                    }
+                }
+                const uint32_t parity = (uses + ((uint32_t)g >> 2)) & 1u;
+                mbar_wait(bars + 8u * (2 * half), parity);
+                mbar_wait(bars + 8u * (2 * half + 1), parity);
 #pragma unroll
                 for (int gg = 0; gg < 2; gg++) {
-                    const uint4 *stage = ring + (size_t)((2 * half + gg) & (kM4rStages - 1)) * kV4;   // (g + gg) % 4, g4 % 4 == 0
+                    const uint32_t stage = ring_c + (uint32_t)(2 * half + gg) * kStage;    // (g + gg) % 4, g4 % 4 == 0
 #pragma unroll
                     for (int t = 0; t < TPF; t++) {
-                        const uint32_t v = (vw[t] >> (8 * (2 * half + gg))) & 0xffu;
-                        const uint4 e = stage[v * 8];
+                        const int sh = 8 * (2 * half + gg);
+                        const uint32_t voff = sh >= 7 ? (vw[t] >> (sh - 7)) & 0x7f80u : (vw[t] << (7 - sh)) & 0x7f80u;   // byte * 128
+                        const uint4 e = lds128(stage + voff);
                         acc[t].x ^= e.x; acc[t].y ^= e.y; acc[t].z ^= e.z; acc[t].w ^= e.w;
                     }
                 }
             }
         }
+        uses += (uint32_t)G >> 2;
         // parity symbols of this row block: 8 lanes of a frame write 128 contiguous bytes per store
 #pragma unroll
         for (int t = 0; t < TPF; t++) {
@@ -181,7 +246,6 @@ encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
                     __stcs(dst + 8 * (16 * i + s2),
                            make_float4(bpsk_bit(w4[i], 2 * s2), 0.f, bpsk_bit(w4[i], 2 * s2 + 1), 0.f));
         }
-        cp_async_wait<0>();
     }
 }
 

@@ -179,9 +179,9 @@ int finish_create(ldpc535_code *c)
 
     // large codes: the look-up encoder's table, built on the device from the column masks
     if (const char *e = getenv("LDPC535_ENCODER")) c->use_m4r = strcmp(e, "generic") != 0;
-    if (t.M % kM4rRows == 0 && t.K % 32 == 0 && t.M >= kM4rRows && (t.K / 32) % (t.M / kM4rRows) == 0 &&
+    if (t.M % kM4rRows == 0 && t.K % 128 == 0 && t.M >= kM4rRows && (t.K / 32) % (t.M / kM4rRows) == 0 &&
         encode_m4r_table_bytes(t.M, t.K) <= ((size_t)512 << 20) &&
-        (size_t)kM4rStages * kM4rStageBytes <= c->smem_optin) {
+        encode_m4r_smem_bytes<8>() <= c->smem_optin) {
         CU(cudaMalloc(reinterpret_cast<void **>(&c->d_m4r), encode_m4r_table_bytes(t.M, t.K)));
         encode_m4r_build_kernel<<<(t.M / kM4rRows) * (t.K / 8), 32>>>(c->d_Pt, c->d_m4r, t.M, t.K, t.mwords);
         CU(cudaGetLastError());
@@ -419,7 +419,7 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
         const long long warps = ((long long)n_frames + 31) / 32;
         const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)c->sm_count * 8);
         encode_small_kernel<<<grid, 256, 0, st>>>(p);
-    } else if (c->d_m4r && c->use_m4r && n_frames >= 256 && (reinterpret_cast<uintptr_t>(d_in) & 3) == 0 &&
+    } else if (c->d_m4r && c->use_m4r && n_frames >= 256 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
         // look-up encoder; batches are cut so that the kernel's 32-bit frame offsets hold
         const long long sms = c->sm_count, rbs = t.M / kM4rRows;
@@ -433,7 +433,7 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
             const int tpf = units_of(8) >= 2 * sms ? 8 : units_of(4) >= 2 * sms ? 4 : units_of(2) >= sms ? 2 : 1;
             void (*kern)(const EncodeParams, const uint4 *) =
                 tpf == 8 ? encode_m4r_kernel<8> : tpf == 4 ? encode_m4r_kernel<4> : tpf == 2 ? encode_m4r_kernel<2> : encode_m4r_kernel<1>;
-            const size_t smem = (size_t)kM4rStages * kM4rStageBytes;
+            const size_t smem = tpf == 8 ? encode_m4r_smem_bytes<8>() : tpf == 4 ? encode_m4r_smem_bytes<4>() : tpf == 2 ? encode_m4r_smem_bytes<2>() : encode_m4r_smem_bytes<1>();
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
             kern<<<(int)std::min<long long>(units_of(tpf), sms), kM4rThreads, smem, st>>>(q, reinterpret_cast<const uint4 *>(c->d_m4r));
