@@ -84,7 +84,8 @@ __device__ __forceinline__ float bpsk_bit(uint32_t word, int b)
 // TPF frames per thread slot: a tile is 128 * TPF frames; the unit of work is (tile, row block), so
 // a CTA's accumulators are 128 bytes per frame and the units spread evenly over the SMs.  A unit
 // also writes its share of the data half of the codeword (K/8 / RB input bytes per frame: one
-// 4-byte word = 256 bytes of symbols every 4 RB-th step), so its stores are spread over its steps.
+// 4-byte word = 256 bytes of symbols per barrier interval), so those stores are spread over its
+// steps: an SM drains stores at ~32 B/clk and a burst stalls every warp behind the next barrier.
 //
 // Data movement: the table stages T[rb][g][*] (32 KB each) arrive by 1-D TMA bulk copies issued
 // by one thread, each completing on its own mbarrier (4-slot ring, two stages consumed per CTA
@@ -92,7 +93,7 @@ __device__ __forceinline__ float bpsk_bit(uint32_t word, int b)
 // per frame at a time with cp.async, one chunk ahead, so that no global-load latency sits in the
 // look-up loop.  All per-frame addresses are 32-bit offsets from the kernel's base pointers (the
 // host splits batches so that they fit); shared memory is addressed with 32-bit offsets too.
-// Requires K % 128 == 0, M % 1024 == 0, (K/32) % (M/1024) == 0, p.in and p.out 16-byte aligned,
+// Requires K % 128 == 0, M % 1024 == 0, M >= 4096 (TPF <= 2 M/1024), (K/32) % (M/1024) == 0, p.in and p.out 16-byte aligned,
 // n_frames * K/32 < 2^32 and n_frames * N / 2 < 2^32.
 // Shared memory: ring[4][32 KB] | input chunks [2][TPF][128][16 B] | 4 mbarriers.
 template <int TPF>
@@ -188,6 +189,8 @@ encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
         uint4 acc[TPF];
 #pragma unroll
         for (int t = 0; t < TPF; t++) acc[t] = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t n_pairs = sys_words * TPF;                  // (frame, data word) pairs of the unit, <= G / 2
+        uint32_t sysw = tmax > 0 ? __ldg(inw + (in0 + rb * sys_words)) : 0u;   // data word written out next
         for (int g4 = 0; g4 < G; g4 += 4) {
             uint32_t vw[TPF];                                      // input bytes g4 .. g4+3 of this slot's frames
 #pragma unroll
@@ -201,19 +204,26 @@ encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
                     const uint32_t ia = in_s + (uint32_t)((g4 >> 4) & 1) * kInBuf + (uint32_t)slot * 16u + (uint32_t)(g4 & 12);
 #pragma unroll
                     for (int t = 0; t < TPF; t++) vw[t] = lds32(ia + (uint32_t)t * kM4rSlots * 16u);
-                    if (((uint32_t)g4 >> 2) % (uint32_t)RB == 0) {
-                        // data half: word sw of the frame = 32 symbols = 16 float4; lane c writes float4 c and c + 8
-                        const uint32_t sw = rb * sys_words + ((uint32_t)g4 >> 2) / (uint32_t)RB;
-                        const int b0 = 8 * (c >> 2) + 7 - 2 * (c & 3);     // symbol j of the word is bit 8 (j / 8) + 7 - j % 8
-#pragma unroll
-                        for (int t = 0; t < TPF; t++) {
-                            if (t < tmax) {
-                                const uint32_t w = __ldg(inw + (in0 + (uint32_t)t * kM4rSlots * in_wstride + sw));
-                                float4 *dst = outq + (out0 + (uint32_t)t * kM4rSlots * out_qstride + ((uint32_t)p.M >> 1) + 16u * sw + c);
-                                __stcs(dst, make_float4(bpsk_bit(w, b0), 0.f, bpsk_bit(w, b0 - 1), 0.f));
-                                __stcs(dst + 8, make_float4(bpsk_bit(w, b0 + 16), 0.f, bpsk_bit(w, b0 + 15), 0.f));
-                            }
+                }
+                // data half, spread thinly: one (frame, word) pair = 32 symbols = 16 float4 per barrier interval
+                // (lane c writes float4 c and c + 8); pair k of the unit is frame t = k % TPF, word k / TPF.
+                // The word of the next pair is fetched one interval ahead of its use.
+                {
+                    const uint32_t k = (uint32_t)g >> 1;
+                    if (k < n_pairs) {
+                        const int t = (int)(k % TPF);
+                        if (t < tmax) {
+                            const uint32_t sw = rb * sys_words + k / TPF;
+                            const int b0 = 8 * (c >> 2) + 7 - 2 * (c & 3);         // symbol j of the word is bit 8 (j / 8) + 7 - j % 8
+                            float4 *dst = outq + (out0 + (uint32_t)t * kM4rSlots * out_qstride + ((uint32_t)p.M >> 1) + 16u * sw + c);
+                            __stcs(dst, make_float4(bpsk_bit(sysw, b0), 0.f, bpsk_bit(sysw, b0 - 1), 0.f));
+                            __stcs(dst + 8, make_float4(bpsk_bit(sysw, b0 + 16), 0.f, bpsk_bit(sysw, b0 + 15), 0.f));
                         }
+                    }
+                    if (k + 1 < n_pairs) {
+                        const int t2 = (int)((k + 1) % TPF);
+                        if (t2 < tmax)
+                            sysw = __ldg(inw + (in0 + (uint32_t)t2 * kM4rSlots * in_wstride + rb * sys_words + (k + 1) / TPF));
                     }
                 }
                 const uint32_t parity = (uses + ((uint32_t)g >> 2)) & 1u;

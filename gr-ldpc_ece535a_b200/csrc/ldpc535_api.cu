@@ -179,7 +179,7 @@ int finish_create(ldpc535_code *c)
 
     // large codes: the look-up encoder's table, built on the device from the column masks
     if (const char *e = getenv("LDPC535_ENCODER")) c->use_m4r = strcmp(e, "generic") != 0;
-    if (t.M % kM4rRows == 0 && t.K % 128 == 0 && t.M >= kM4rRows && (t.K / 32) % (t.M / kM4rRows) == 0 &&
+    if (t.M % kM4rRows == 0 && t.K % 128 == 0 && t.M >= 4 * kM4rRows && (t.K / 32) % (t.M / kM4rRows) == 0 &&
         encode_m4r_table_bytes(t.M, t.K) <= ((size_t)512 << 20) &&
         encode_m4r_smem_bytes<8>() <= c->smem_optin) {
         CU(cudaMalloc(reinterpret_cast<void **>(&c->d_m4r), encode_m4r_table_bytes(t.M, t.K)));
