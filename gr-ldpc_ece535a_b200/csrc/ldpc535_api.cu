@@ -419,7 +419,8 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
         const long long warps = ((long long)n_frames + 31) / 32;
         const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)c->sm_count * 8);
         encode_small_kernel<<<grid, 256, 0, st>>>(p);
-    } else if (c->d_m4r && c->use_m4r && n_frames >= 256 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
+    // look-up encoder from ~3 k frames on (measured cross-over with the scan kernel: 2 k..4 k frames)
+    } else if (c->d_m4r && c->use_m4r && n_frames >= 3072 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
         // look-up encoder; batches are cut so that the kernel's 32-bit frame offsets hold
         const long long sms = c->sm_count, rbs = t.M / kM4rRows;
