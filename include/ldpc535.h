@@ -189,8 +189,12 @@ LDPC535_API int ldpc535_decode_debug(ldpc535_code *code, const float *sym, size_
                                      float *out_L, float *out_E, float *out_M,
                                      uint8_t *out_bytes, uint8_t *out_iters);
 
-/* Force a kernel family for subsequent decode calls ("warp", "block", "c4-thread",
- * NULL/"auto" = default).  Returns LDPC535_ERR_UNSUPPORTED if the code cannot run on it. */
+/* Force a kernel family for subsequent decode calls ("warp", "block", "c4-thread", "regular",
+ * NULL/"auto" = default).  Returns LDPC535_ERR_UNSUPPORTED if the code cannot run on it.
+ * Measurement knobs read from the environment at ldpc535_code_create* (results never change):
+ * LDPC535_REGULAR_VARIANT=0 runs the (3,6)-regular n = 8192 code on the 1024-thread kernel instead
+ * of the register-table one; LDPC535_ENCODER=generic keeps large codes on the AND/XOR scan encoder
+ * instead of the table look-up one. */
 LDPC535_API int ldpc535_code_set_kernel(ldpc535_code *code, const char *kernel);
 
 /* How ldpc535_decode_batch moves host symbols to the device.  Pageable input is always staged
