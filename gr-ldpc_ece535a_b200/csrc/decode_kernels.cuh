@@ -42,6 +42,8 @@ struct DecodeParams {
     // block kernel: table staging
     int stage_tables;             // 1: copy chk_var / var_slot into shared memory
     int tabA_bytes, tabB_bytes;   // padded to 16 B
+    // register-table regular kernel: windows are handed out by an atomic cursor (starts at 0)
+    unsigned int *cursor;
 };
 
 constexpr int kWarpKernelThreads = 128;

@@ -220,16 +220,24 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
 
     const bool tag = p.early_stop != 0;
     const uint32_t tagmask = tag ? 0x40000000u : 0u;
-    for (long long w = blockIdx.x; w < p.n_win; w += gridDim.x) {
+    // Windows are handed out by an atomic cursor, one ahead: iteration counts differ from codeword to
+    // codeword under early stop, so fixed shares would leave SMs idle at the end of the batch (the
+    // mean over 54 codewords per CTA still spreads by a few percent; small batches by much more).
+    // red[1] carries the next window of the CTA; window k < gridDim.x goes to CTA k without an atomic.
+    long long w = blockIdx.x;
+    while (w < p.n_win) {
+        if (tid == 0) red[1] = (int)(gridDim.x + atomicAdd(p.cursor, 1u));
         const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
         const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
         const bool ok = off >= 0 && off + N <= p.n_sym;
         float r[BQ];
 #pragma unroll
         for (int q = 0; q < BQ; q++) r[q] = ok ? (-pol * kSpaScale) * load_re(p, off + q * NT + tid) : 0.f;
+        __syncthreads();                                   // previous window fully drained; red[1] visible
+        const long long w_next = (long long)(unsigned int)red[1];
         // pull the next window of this CTA towards L2 while this one iterates (one 128-byte line per thread)
-        if (w + gridDim.x < p.n_win) {
-            const long long offn = p.win_offset ? p.win_offset[w + gridDim.x] : (w + gridDim.x) * (long long)N;
+        if (w_next < p.n_win) {
+            const long long offn = p.win_offset ? p.win_offset[w_next] : w_next * (long long)N;
             if (offn >= 0 && offn + N <= p.n_sym) {
                 const char *base = p.sym_re ? reinterpret_cast<const char *>(p.sym_re + offn)
                                             : reinterpret_cast<const char *>(p.sym + offn);
@@ -237,7 +245,6 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
                 if (tid * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + tid * 128));
             }
         }
-        __syncthreads();                                   // previous window fully drained
         if (tid == 0) red[0] = 0;
         // M_ji = r_i on every edge, stored as t = copysign(2^-|M|, M), no tags yet
 #pragma unroll
@@ -319,6 +326,7 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
             if (p.out_synd) p.out_synd[w] = ok ? (uint8_t)min(cnt, p.thr + 1) : (uint8_t)255;
             if (p.out_iters) p.out_iters[w] = ok ? (uint8_t)min(iters, 255) : (uint8_t)255;
         }
+        w = w_next;
     }
 }
 

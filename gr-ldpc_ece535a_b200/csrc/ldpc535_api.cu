@@ -74,6 +74,8 @@ struct ldpc535_code {
     uint16_t *d_w_chk_pos = nullptr, *d_w_var_pos = nullptr;   // warp kernel strip layout
     int32_t *d_w_pos_edge = nullptr;
     uint16_t *d_var_row4 = nullptr;   // [N][4] message addresses of a bit (regular codes, dv <= 4)
+    unsigned int *d_cursor = nullptr; // window cursors of the register-table kernel (one per launch in flight, round-robin)
+    unsigned int cursor_launch = 0;
     bool fits_regular = false;
     int regular_variant = 1;          // 1: 512-thread register-table kernel (fixed sizes), 0: 1024-thread kernel
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
@@ -247,7 +249,7 @@ void release(ldpc535_code *c)
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
-    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_cursor); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
     delete c;
 }
 
@@ -383,6 +385,11 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
         const bool fixed8k = c->t.M == 4096 && c->t.N == 8192 && c->block_threads == 1024;
         const int grid = (int)std::min<long long>(p.n_win, (long long)c->sm_count);
         if (fixed8k && c->regular_variant == 1) {
+            if (!c->d_cursor && cudaMalloc(reinterpret_cast<void **>(&c->d_cursor), 64 * sizeof(unsigned int)) != cudaSuccess)
+                return fail(LDPC535_ERR_CUDA, "cursor allocation");
+            p.cursor = c->d_cursor + (c->cursor_launch++ & 63u);          // zeroed on the stream just before its launch
+            if ((e = cudaMemsetAsync(p.cursor, 0, sizeof(unsigned int), st)) != cudaSuccess)
+                return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
             auto kern = decode_regular_rt_kernel<6, 3, 4096, 8192>;
             const size_t smem = regular_rt_smem_bytes<6, 4096, 8192>();
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
