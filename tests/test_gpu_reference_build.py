@@ -135,6 +135,31 @@ def test_block_forecasts_match_reference_build(g):
 
 
 # ---------------------------------------------------------------------------------------------
+# BASELINE config 4's n = 8192 code against the reference's own decode members (committed outputs)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", ["1", "0"])
+def test_c8k_decisions_match_reference_build(monkeypatch, variant):
+    """decodeSumProductSoft / decodeLogDomainSimple of lib/ldpc_decoder_cb_impl.cc on the 4096 x 8192
+    matrix (tools/gen_ref_golden_c8k.py) vs the CTA-per-codeword kernels: data bytes of the decision and
+    checkFrame(v, M/8), for both (3,6)-regular kernel variants and the generic block kernel (min-sum)."""
+    g8 = np.load(os.path.join(GOLD, "ref_build_c8k.npz"))
+    monkeypatch.setenv("LDPC535_REGULAR_VARIANT", variant)
+    rp, ci, M, N = L.codes.regular_code(8192, 3, 6, int(g8["seed"]))
+    code = L.Code((rp, ci, M, N), device=0)
+    sym = g8["rx"].astype(np.complex64)
+    sent = np.unpackbits(g8["sent"], axis=1)[:, :N]
+    assert np.array_equal(code.encode(np.packbits(sent[:, M:], axis=1))[:, :].real.reshape(-1, N) > 0, sent == 1)
+    for name, method, iters in (("spa3", 1, 3), ("spa12", 1, 12), ("minsum8", 0, 8)):
+        want = np.unpackbits(g8[name + "_vhat"], axis=1)[:, :N]
+        b, sy, _ = code.decode(sym, method=method, max_iters=iters, early_stop=True)
+        assert np.array_equal(b, np.packbits(want[:, M:], axis=1)), name
+        # one byte per window: the C ABI caps the threshold at 253, so the weight saturates at 254
+        assert np.array_equal(sy.astype(np.int32), np.minimum(g8[name + "_synd"], 254)), name
+    code.close()
+
+
+# ---------------------------------------------------------------------------------------------
 # live: the prebuilt reference library on the GPU box
 # ---------------------------------------------------------------------------------------------
 

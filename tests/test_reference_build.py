@@ -8,6 +8,7 @@ oracle/refshim/ (oracle/ref_driver.cc, oracle/Makefile).  Two layers:
   (tools/gen_ref_golden.py) -- run everywhere, including where /root/reference does not exist;
 * `live` tests call the library itself on wider sweeps and are skipped where it is not built.
 """
+import hashlib
 import json
 import os
 
@@ -142,6 +143,61 @@ def test_forecasts_match_reference_build(g):
     # decoder asks noutput*N (lib/ldpc_decoder_cb_impl.cc:126-130), encoder ceil(nout/16) (:111-116)
     assert list(g["dec_forecast"]) == [n * 64 for n in (1, 4, 64, 4096)]
     assert list(g["enc_forecast"]) == [int(np.ceil(n / 16.0)) for n in (1, 16, 17, 64, 640, 4096)]
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4's (3,6)-regular n = 8192 code: the reference's reorderHMatrix and decode members on
+# 4096 x 8192 dense matrices (tools/gen_ref_golden_c8k.py; ~4 s per iteration and codeword there)
+# ---------------------------------------------------------------------------------------------
+
+def sha_bits(a):
+    return hashlib.sha256(np.packbits(np.asarray(a, np.uint8), axis=1).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def g8k():
+    return np.load(os.path.join(GOLD, "ref_build_c8k.npz"))
+
+
+@pytest.fixture(scope="module")
+def c8k_host(g8k):
+    """The product's host tables for the same seeded code (LDPC535_DEVICE_NONE: no compute)."""
+    import ldpc_ece535a as L
+    rp, ci, M, N = L.codes.regular_code(8192, 3, 6, int(g8k["seed"]))
+    code = L.Code((rp, ci, M, N), device=-1)
+    yield code, L.codes.to_dense(rp, ci, M, N)
+    code.close()
+
+
+def test_c8k_reorder_matches_reference_build(g8k, c8k_host):
+    """Column re-ordering and LU factors of the 4096 x 8192 matrix: the library's bit-packed GF(2)
+    elimination and the oracle's dense one against the reference's reorderHMatrix."""
+    code, H = c8k_host
+    assert sha_bits(code.h_dense()) == str(g8k["Hp_sha256"])
+    assert np.array_equal(code.h_dense().sum(0)[:64], g8k["Hp_col_weight_head"])
+    Hp, Lm, Um, piv = O.reorder_h(H)
+    assert sha_bits(Hp) == str(g8k["Hp_sha256"])
+    assert sha_bits(Lm) == str(g8k["L_sha256"]) and int(Lm.sum()) == int(g8k["L_nnz"])
+    assert sha_bits(Um) == str(g8k["U_sha256"]) and int(Um.sum()) == int(g8k["U_nnz"])
+    assert np.array_equal(code.pivots(), piv)
+
+
+@pytest.mark.parametrize("name,method,iters", [("spa3", 1, 3), ("spa12", 1, 12), ("minsum8", 0, 8)])
+def test_c8k_sparse_oracle_matches_reference_build(g8k, c8k_host, name, method, iters):
+    """Decisions of the reference's dense decodeSumProductSoft / decodeLogDomainSimple on the n = 8192
+    code == the sparse restatement the GPU tests use at this size."""
+    code, _ = c8k_host
+    if method != 1:
+        pytest.skip("the sparse restatement covers sum-product; min-sum at this size is checked on the GPU")
+    row_ptr, col_idx = code.h_csr()
+    rows = np.repeat(np.arange(code.M), np.diff(row_ptr))
+    order = np.lexsort((rows, col_idx))
+    col_ptr = np.zeros(code.N + 1, np.int32)
+    np.add.at(col_ptr, col_idx + 1, 1)
+    tables = (row_ptr, col_idx, np.cumsum(col_ptr).astype(np.int32), order.astype(np.int32))
+    for f in range(g8k["rx"].shape[0]):
+        vhat, run = O.decode_spa_sparse(g8k["rx"][f].astype(np.float64), tables, code.M, code.N, iters, True)
+        assert np.array_equal(np.packbits(vhat.astype(np.uint8)), g8k[name + "_vhat"][f]), (name, f)
 
 
 # ---------------------------------------------------------------------------------------------
