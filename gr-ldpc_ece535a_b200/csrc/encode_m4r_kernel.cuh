@@ -157,6 +157,7 @@ encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
     }
     __syncthreads();
     uint32_t uses = 0;                                             // completed phases of every ring slot
+    const bool early = ((tid >> 7) & 1) != 0;                      // warps 4-7, 12-15, ..: stores before the look-ups
 
     for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const uint32_t tile = unit / (uint32_t)RB;
@@ -208,7 +209,7 @@ encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
                 // data half, spread thinly: one (frame, word) pair = 32 symbols = 16 float4 per barrier interval
                 // (lane c writes float4 c and c + 8); pair k of the unit is frame t = k % TPF, word k / TPF.
                 // The word of the next pair is fetched one interval ahead of its use.
-                {
+                auto store_data_half = [&]() {
                     const uint32_t k = (uint32_t)g >> 1;
                     if (k < n_pairs) {
                         const int t = (int)(k % TPF);
@@ -225,7 +226,12 @@ encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
                         if (t2 < tmax)
                             sysw = __ldg(inw + (in0 + (uint32_t)t2 * kM4rSlots * in_wstride + rb * sys_words + (k + 1) / TPF));
                     }
-                }
+                };
+                // One SM drains stores at 32 B/clk (tools/microbench/store_rate.cu), and a warp whose store waits
+                // for that path also holds back its own shared-memory reads behind it (in-order MIO queue).  After
+                // a CTA barrier all warps sit at the same program point, so half of the warps of every
+                // sub-partition issue the stores of the interval before its look-ups, the other half after them.
+                if (early) store_data_half();
                 const uint32_t parity = (uses + ((uint32_t)g >> 2)) & 1u;
                 mbar_wait(bars + 8u * (2 * half), parity);
                 mbar_wait(bars + 8u * (2 * half + 1), parity);
@@ -240,6 +246,7 @@ encode_m4r_kernel(const EncodeParams p, const uint4 *__restrict__ T)
                         acc[t].x ^= e.x; acc[t].y ^= e.y; acc[t].z ^= e.z; acc[t].w ^= e.w;
                     }
                 }
+                if (!early) store_data_half();
             }
         }
         uses += (uint32_t)G >> 2;
