@@ -15,9 +15,16 @@ torch.distributed is only the barrier and the max-over-ranks of the device time.
   e2e       the call a block's work() makes: ldpc535_decode_batch on PINNED HOST buffers,
             H2D of the symbols and D2H of bytes / syndrome weights / iteration counts inside
             the timed region.
-  roofline  HBM bytes of the decode kernel against the measured copy bandwidth (the schema's
-            bound) plus `governing`: the SM special-function / issue roofline that actually
-            bounds a 50-iteration sum-product (DESIGN.md "Rooflines").
+  roofline  the roofline that governs a 50-iteration sum-product: executed MUFU operations per
+            second against the SM special-function pipe's ceiling MEASURED IN THE SAME RUN
+            (ldpc535_probe_pipe_peak); the HBM figure (algorithmic bytes against the measured copy
+            bandwidth, ~1 %) sits beside it under `hbm` (DESIGN.md "Rooflines").
+  configs   (one GPU only) the other BASELINE configs and kernels, each with its own roofline:
+            the shipped code at the reference block's settings (5 iterations, early stop) at
+            2 / 4 / 6 dB, min-sum, hard decision, both encoders, and configs[3] -- the
+            (3,6)-regular n = 8192 code with early termination over batches of 1 k ... 1 M.
+  inputs    counter-based: Philox4x32-10, seed 535, counter = GLOBAL codeword index, so the
+            shard of rank r (codewords r*n .. (r+1)*n) is the same at any GPU count.
   cpu_baseline  oracle/_ref -- the reference's own decoder sources compiled against dependency
             stand-ins (`kind: reference`) -- on all host cores, on a bounded sample of the same
             workload; beside it (`port_same_work`) the oracle port running exactly the GPU arm's
@@ -48,9 +55,11 @@ BYTES_PER_CW = 8 * N_SYM + K_INFO // 8 + 2          # complex64 in + 
 XU_PER_EDGE_ITER = 4                                # SURVEY 8d algorithmic figure (tanh, log, div)
 MUFU_PER_EDGE_ITER = 3                              # what the kernels execute: 1 ex2 + 2 lg2 (spa_math.cuh)
 SM_COUNT, XU_LANES = 148, 16
-# XU-pipe ceiling measured on this pool's B200 with tools/microbench/mufu_peak.cu (independent
-# ex2/lg2 streams, 1 ex2 : 2 lg2 mix): 15.9 MUFU lanes/clk/SM at 1965 MHz (profiles/r1_microbench.txt)
-XU_MEASURED_PEAK = 4.63e12
+# (the XU-pipe ceiling is measured in every run by ldpc535_probe_pipe_peak: 1 ex2 : 2 lg2 mix)
+# Min-sum (fp64, decode_warp_kernel<0,6,3>): warp instructions per codeword and iteration, counted in
+# the SASS of the iteration loop (tools/sass_count.py): 239 in all, 51 of them on the fp64 pipe.
+MINSUM_INSTR_PER_CW_ITER = 239
+MINSUM_FP64_PER_CW_ITER = 51
 
 
 def config(n_cw, n_gpus):
@@ -181,7 +190,45 @@ def cpu_baseline(per_core):
     return {"value": n * K_INFO / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "reference",
             "sample": "%d codewords (%d per core, one pinned thread per core) of the same workload, %s, "
                       "%.1f s" % (n, per_core, REF_NOTE, dt),
-            "codewords_per_s": n / dt, "port_same_work": port}
+            "codewords_per_s": n / dt, "port_same_work": port, "encoder": ref_encoder_baseline(cores, per_core)}
+
+
+def ref_encoder_baseline(cores, per_core):
+    """The reference's encoder block (lib/ldpc_encoder_bc_impl.cc:118-178: general_work ->
+    makeParityCheck :275-294 -> solve/dgesv :180-223, compiled from its sources in oracle/_ref),
+    one block instance per pinned host thread, on per_core frames each."""
+    import numpy as np
+    from oracle import ref as R
+    rng = np.random.default_rng(535)
+    data = rng.integers(0, 256, (cores, per_core * 4)).astype(np.uint8)
+    encs = [R.RefEncoder() for _ in range(cores)]
+    cpus = sorted(os.sched_getaffinity(0))
+
+    def worker(t):
+        try:
+            os.sched_setaffinity(0, {cpus[t % len(cpus)]})
+        except OSError:
+            pass
+        done = 0
+        while done < per_core:                        # general_work-sized calls, like a scheduler would make
+            n = min(4096, per_core - done)
+            encs[t].work(data[t, done * 4:(done + n) * 4], n * N_SYM)
+            done += n
+
+    worker_threads = [threading.Thread(target=worker, args=(t,)) for t in range(cores)]
+    t0 = time.perf_counter()
+    for th in worker_threads:
+        th.start()
+    for th in worker_threads:
+        th.join()
+    dt = time.perf_counter() - t0
+    for e in encs:
+        e.close()
+    n = cores * per_core
+    return {"value": n * K_INFO / dt / 1e9, "unit": "Gbit/s info", "frames_per_s": n / dt, "cores": cores,
+            "kind": "reference",
+            "sample": "%d frames (%d per core) through the reference's ldpc_encoder_bc::general_work "
+                      "(oracle/_ref), %.2f s" % (n, per_core, dt)}
 
 
 def run_reference(args):
@@ -221,6 +268,9 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+SEED = 535                                   # Philox, seed 535, counter = global codeword index
+
+
 def pinned_array(L, nbytes, dtype, shape):
     import numpy as np
     from ldpc_ece535a import _abi
@@ -228,6 +278,209 @@ def pinned_array(L, nbytes, dtype, shape):
     _abi.check(_abi.lib().ldpc535_host_alloc(nbytes, C.byref(p)), "host_alloc")
     buf = (C.c_uint8 * nbytes).from_address(p.value)
     return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+def bind_near_gpu(local):
+    """Best effort: restrict this rank to the host cores local to its GPU (sysfs local_cpulist of
+    the GPU's PCI function), so pinned buffers are first-touched on, and the packing team runs on,
+    the GPU's own NUMA node.  -> description for the JSON line."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        have = os.sched_getaffinity(0)
+        near = cpus & have
+        if near and len(near) < len(have):
+            os.sched_setaffinity(0, near)
+            return "bound to the %d cores local to GPU %s (of %d)" % (len(near), bdf, len(have))
+        return "all %d cores are local to GPU %s" % (len(have), bdf)
+    except Exception as e:            # no sysfs entry in a VM, older torch: leave the affinity alone
+        return "not bound (%s)" % type(e).__name__
+
+
+def synth_shard(code, first_frame, n, ebn0_db, stream_ptr, d_data=None, d_sym=None):
+    """Frames first_frame .. first_frame + n of the seeded stream, on the device: Philox data bytes ->
+    the library's encoder -> AWGN on the real axis (sigma^2 = 10^(-EbN0/10))."""
+    import numpy as np
+    import torch
+    if d_data is None:
+        d_data = torch.empty((n, code.nbytes), dtype=torch.uint8, device="cuda")
+    if d_sym is None:
+        d_sym = torch.empty((n, code.N, 2), dtype=torch.float32, device="cuda")
+    code.synth_bytes_dev(SEED, first_frame, n, d_data.data_ptr(), stream=stream_ptr)
+    code.encode_dev(d_data.data_ptr(), n, d_sym.data_ptr(), stream=stream_ptr)
+    if ebn0_db is not None:
+        sigma = float(np.sqrt(10.0 ** (-ebn0_db / 10.0)))
+        code.synth_awgn_dev(SEED, first_frame, n, sigma, d_sym.data_ptr(), stream=stream_ptr)
+    return d_data, d_sym
+
+
+def time_launches(stream, fn, steps, warmup):
+    """ms per call of fn(), CUDA events on the launching stream, after warm-up."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(steps):
+        fn()
+    b.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def traffic_from_profiles(kernel):
+    """DRAM bytes per codeword of `kernel` from the committed ncu --set full summary
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the capture named in it)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        e = t["kernels"].get(kernel)
+        return (e["dram_bytes_per_codeword"], e.get("source")) if e else (None, None)
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
+def extra_configs(L, torch, np, c4, stream, sp, d_data, d_sym, n_cw, first_frame, mufu_peak, fp64_peak, hbm_peak, f_max):
+    """The other BASELINE configs and kernels, device-resident, same timing method as `value`
+    (CUDA events on the launching stream, warm-up first, inputs larger than L2 except where the
+    batch size itself is the point).  One GPU only."""
+    out = {}
+    d_bytes = torch.empty((n_cw, 4), dtype=torch.uint8, device="cuda")
+    d_synd = torch.empty(n_cw, dtype=torch.uint8, device="cuda")
+    d_iters = torch.empty(n_cw, dtype=torch.uint8, device="cuda")
+
+    # ---- configs[0]: the shipped code at the reference block's own settings (5 iterations, early stop) ----
+    rows = []
+    for ebn0 in (2.0, 4.0, 6.0):
+        synth_shard(c4, first_frame, n_cw, ebn0, sp, d_data, d_sym)
+        for method, name in ((L.METHOD_SUMPRODUCT, "sum-product"), (L.METHOD_LOGDOMAIN, "min-sum (GRC default)")):
+            if method == L.METHOD_LOGDOMAIN and ebn0 != 2.0:
+                continue
+
+            def one():
+                c4.decode_dev(d_sym.data_ptr(), n_cw * N_SYM, n_cw, d_bytes.data_ptr(), d_synd.data_ptr(),
+                              d_iters.data_ptr(), method=method, max_iters=5, early_stop=True, stream=sp)
+            ms = time_launches(stream, one, 3, 2)
+            it_sum = float(d_iters.sum(dtype=torch.float64).item())
+            row = {"method": name, "ebn0_db": ebn0, "max_iters": 5, "early_stop": 1, "codewords": n_cw,
+                   "kernel": c4.kernel_name(method), "ms": ms, "gbit_s": n_cw * K_INFO / ms / 1e6,
+                   "mean_iters": it_sum / n_cw,
+                   "frames_recovered": float((d_bytes == d_data).all(dim=1).float().mean().item())}
+            eit = it_sum * E_EDGES / (ms * 1e-3)
+            row["edge_iterations_per_s"] = eit
+            if method == L.METHOD_SUMPRODUCT:
+                # + the start-up exponentials (one ex2 per bit) each codeword pays once
+                mufu = (MUFU_PER_EDGE_ITER * it_sum * E_EDGES + n_cw * N_SYM) / (ms * 1e-3)
+                row["roofline"] = {"bound": "sm_xu", "achieved": mufu / 1e12, "peak": mufu_peak / 1e12,
+                                   "unit": "T MUFU/s", "frac": mufu / mufu_peak}
+            else:
+                # min-sum runs in fp64; its loop is 239 warp instructions per codeword and iteration, so
+                # the issue slots (1 warp instruction per clock and SM sub-partition) bound it before the
+                # fp64 pipe does (51 of the 239, 2 clocks each at the measured fp64 rate)
+                wi = MINSUM_INSTR_PER_CW_ITER * it_sum / (ms * 1e-3)
+                issue_peak = SM_COUNT * 4 * f_max
+                fp64_ops = MINSUM_FP64_PER_CW_ITER * 32 * it_sum / (ms * 1e-3)
+                row["roofline"] = {"bound": "sm_issue", "achieved": wi / 1e12, "peak": issue_peak / 1e12,
+                                   "unit": "T warp-instr/s", "frac": wi / issue_peak,
+                                   "fp64_pipe": {"achieved": fp64_ops / 1e12, "peak": fp64_peak / 1e12,
+                                                 "unit": "T thread-instr/s", "frac": fp64_ops / fp64_peak},
+                                   "def": "SASS count of the kernel's iteration loop (tools/sass_count.py): %d warp "
+                                          "instructions per codeword and iteration, %d on the fp64 pipe; issue peak = "
+                                          "148 SMs x 4 schedulers x max SM clock; fp64 peak measured by "
+                                          "ldpc535_probe_pipe_peak (2 DADD : 1 DSETP)"
+                                          % (MINSUM_INSTR_PER_CW_ITER, MINSUM_FP64_PER_CW_ITER)}
+            rows.append(row)
+    out["configs[0] shipped code, reference block settings"] = rows
+
+    # ---- hard decision (method 3): HBM-bound ----
+    def hard():
+        c4.decode_dev(d_sym.data_ptr(), n_cw * N_SYM, n_cw, d_bytes.data_ptr(), d_synd.data_ptr(),
+                      d_iters.data_ptr(), method=L.METHOD_HARD, max_iters=5, early_stop=True, stream=sp)
+    ms = time_launches(stream, hard, 5, 2)
+    gbs = n_cw * BYTES_PER_CW / ms / 1e6
+    out["hard decision (method 3), shipped code"] = {
+        "codewords": n_cw, "kernel": c4.kernel_name(L.METHOD_HARD), "ms": ms, "gbit_s": n_cw * K_INFO / ms / 1e6,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}}
+
+    # ---- encoder, shipped code ----
+    def enc4():
+        c4.encode_dev(d_data.data_ptr(), n_cw, d_sym.data_ptr(), stream=sp)
+    ms = time_launches(stream, enc4, 5, 2)
+    gbs = n_cw * (4 + 8 * N_SYM) / ms / 1e6
+    out["encoder, shipped code"] = {
+        "frames": n_cw, "ms": ms, "gbit_s": n_cw * K_INFO / ms / 1e6,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}}
+    del d_bytes, d_synd, d_iters
+
+    # ---- configs[3]: (3,6)-regular rate-1/2 n = 8192, early termination on, batch sweep ----
+    c8, seed8 = L.codes.first_invertible(n=8192, seed=SEED, device=c4.device)
+    M8, N8, K8, E8 = c8.M, c8.N, c8.K, c8.E
+    nmax = 1_000_000
+    free, _ = torch.cuda.mem_get_info()
+    while nmax > 1000 and nmax * (N8 * 8 + 2 * c8.nbytes + 2) > 0.8 * free:
+        nmax //= 10
+    d8_data, d8_sym = synth_shard(c8, 0, nmax, EBN0_DB, sp)
+    d8_bytes = torch.empty((nmax, c8.nbytes), dtype=torch.uint8, device="cuda")
+    d8_synd = torch.empty(nmax, dtype=torch.uint8, device="cuda")
+    d8_iters = torch.empty(nmax, dtype=torch.uint8, device="cuda")
+    rows = []
+    for nb in (1000, 10_000, 100_000, 1_000_000):
+        if nb > nmax:
+            continue
+
+        def one():
+            c8.decode_dev(d8_sym.data_ptr(), nb * N8, nb, d8_bytes.data_ptr(), d8_synd.data_ptr(),
+                          d8_iters.data_ptr(), method=L.METHOD_SUMPRODUCT, max_iters=MAX_ITERS,
+                          early_stop=True, stream=sp)
+        ms = time_launches(stream, one, 2 if nb >= 1_000_000 else 4, 1 if nb >= 100_000 else 3)
+        it_sum = float(d8_iters[:nb].sum(dtype=torch.float64).item())
+        mufu = (MUFU_PER_EDGE_ITER * it_sum * E8 + nb * N8) / (ms * 1e-3)
+        rows.append({"batch": nb, "ms": ms, "gbit_s": nb * K8 / ms / 1e6, "mean_iters": it_sum / nb,
+                     "edge_iterations_per_s": it_sum * E8 / (ms * 1e-3),
+                     "frames_recovered": float((d8_bytes[:nb] == d8_data[:nb]).all(dim=1).float().mean().item()),
+                     "roofline": {"bound": "sm_xu", "achieved": mufu / 1e12, "peak": mufu_peak / 1e12,
+                                  "unit": "T MUFU/s", "frac": mufu / mufu_peak}})
+    nfix = min(nmax, 20_000)
+
+    def fixed():
+        c8.decode_dev(d8_sym.data_ptr(), nfix * N8, nfix, d8_bytes.data_ptr(), d8_synd.data_ptr(),
+                      d8_iters.data_ptr(), method=L.METHOD_SUMPRODUCT, max_iters=20, early_stop=False, stream=sp)
+    ms = time_launches(stream, fixed, 3, 1)
+    mufu = (MUFU_PER_EDGE_ITER * 20.0 * nfix * E8 + nfix * N8) / (ms * 1e-3)
+    out["configs[3] (3,6)-regular n=8192, seed %d, sum-product, 50 iterations max, early stop on, 2 dB" % seed8] = {
+        "kernel": c8.kernel_name(L.METHOD_SUMPRODUCT), "batches": rows,
+        "fixed_20_iterations": {"codewords": nfix, "ms": ms, "edge_iterations_per_s": 20.0 * nfix * E8 / (ms * 1e-3),
+                                "roofline": {"bound": "sm_xu", "achieved": mufu / 1e12, "peak": mufu_peak / 1e12,
+                                             "unit": "T MUFU/s", "frac": mufu / mufu_peak}}}
+    del d8_bytes, d8_synd, d8_iters
+
+    # ---- encoder, n = 8192 code (table look-up kernel) ----
+    rows = []
+    for nf in (2_000, 20_000, 400_000):
+        if nf > nmax:
+            continue
+
+        def enc8():
+            c8.encode_dev(d8_data.data_ptr(), nf, d8_sym.data_ptr(), stream=sp)
+        ms = time_launches(stream, enc8, 4, 2)
+        gbs = nf * (c8.nbytes + 8 * N8) / ms / 1e6
+        rows.append({"frames": nf, "ms": ms, "gbit_s": nf * K8 / ms / 1e6,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": gbs / hbm_peak}})
+    out["encoder, n=8192 code"] = rows
+    c8.close()
+    return out
 
 
 def run_gpu(args):
@@ -239,36 +492,34 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run" % (args.gpus, world))
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: this benchmark has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    cores_host = len(os.sched_getaffinity(0))
+    numa_note = bind_near_gpu(local) if world > 1 else "single rank: affinity left alone"
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n_cw = args.codewords
+    first_frame = rank * n_cw                # this rank's contiguous shard of the global stream
     code = L.Code(None, device=local)
     if args.kernel:
         code.set_kernel(args.kernel)
+    # the launcher knows how many ranks share the host: give each its share of the cores and let
+    # the handle decide pack-or-raw from that (>= 12 threads: pack) -- unless told otherwise
+    share = max(1, min(cores_host // local_world, len(os.sched_getaffinity(0))))
+    code.set_host_path(args.pack_pinned, args.pack_threads or share)
     stream = torch.cuda.Stream()            # a real stream: NULL would mean "the handle's own"
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
     assert sp.value, "expected a non-default stream"
 
-    # ---- synthetic shard, generated on the device (seed = 535 + global shard index) ----
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(535 + rank)
-    d_data = torch.randint(0, 256, (n_cw, 4), dtype=torch.uint8, device="cuda", generator=gen)
-    d_sym = torch.empty((n_cw, N_SYM, 2), dtype=torch.float32, device="cuda")
-    code.encode_dev(d_data.data_ptr(), n_cw, d_sym.data_ptr(), stream=sp)
-    sigma = float(np.sqrt(10.0 ** (-EBN0_DB / 10.0)))
-    step = 1 << 20
-    for a in range(0, n_cw, step):
-        b = min(n_cw, a + step)
-        d_sym[a:b, :, 0] += sigma * torch.randn((b - a, N_SYM), device="cuda", generator=gen)
+    d_data, d_sym = synth_shard(code, first_frame, n_cw, EBN0_DB, sp)
     d_bytes = torch.empty((n_cw, 4), dtype=torch.uint8, device="cuda")
     d_synd = torch.empty(n_cw, dtype=torch.uint8, device="cuda")
     d_iters = torch.empty(n_cw, dtype=torch.uint8, device="cuda")
@@ -290,6 +541,13 @@ def run_gpu(args):
             return ms
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
     # ---- device-resident timing ----
@@ -317,6 +575,8 @@ def run_gpu(args):
     # correctness guard on the timed output: the decoded shard must mostly equal the data sent
     frame_ok = float((d_bytes == d_data).all(dim=1).float().mean().item())
     bad_iters = int((d_iters != MAX_ITERS).sum().item())
+    # a digest of the shard's data bytes: equal for the same global indices at any GPU count
+    shard_digest = int(d_data.view(torch.int32).to(torch.int64).sum().item()) & 0xFFFFFFFFFFFF
 
     # ---- end to end through the host-buffer C ABI ----
     # The same shard, from pinned host memory.  If the box cannot pin a whole shard (5.1 GB per
@@ -371,6 +631,25 @@ def run_gpu(args):
                  if hp["pack_pinned"] else "copy engine reads the caller's pinned buffer directly")
     pcie_bytes = e2e_cw * world * (256 if hp["pack_pinned"] else 512)
 
+    # ---- the box's host->device ceiling with every rank copying at once: plain pinned copies of the
+    # same buffer in the pipeline's chunk size, no kernel, no packing ----
+    chunk = 128 << 20
+    h2d_total = min(e2e_cw * 512, 2 << 30)
+    d_sink = torch.empty(chunk, dtype=torch.uint8, device="cuda")
+
+    def h2d_sweep():
+        for off in range(0, h2d_total, chunk):
+            _abi.lib().ldpc535_memcpy_h2d(code.handle, d_sink.data_ptr(), C.c_void_p(p1.value + off),
+                                          min(chunk, h2d_total - off))
+    h2d_sweep()
+    barrier()
+    t0 = time.perf_counter()
+    h2d_sweep()
+    h2d_s = max_over_ranks(time.perf_counter() - t0)
+    h2d_ceiling = h2d_total * world / h2d_s / 1e9          # GB/s, all ranks together
+    del d_sink
+
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -381,31 +660,31 @@ def run_gpu(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"
         f_max = float((clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        mufu_peak = code.probe_pipe_peak(_abi.PIPE_MUFU)          # measured now, on this GPU
+        fp64_peak = code.probe_pipe_peak(_abi.PIPE_FP64)
         t_k = kern_ms * 1e-3
         hbm_achieved = n_cw * BYTES_PER_CW / t_k / 1e9
         edge_it = n_cw * E_EDGES * MAX_ITERS / t_k
-        xu_peak_ops = SM_COUNT * XU_LANES * f_max
+        mufu = (MUFU_PER_EDGE_ITER * n_cw * E_EDGES * MAX_ITERS + n_cw * N_SYM) / t_k
+        xu_nominal = SM_COUNT * XU_LANES * f_max
+        kname = code.kernel_name(L.METHOD_SUMPRODUCT)
+        per_cw, tsrc = traffic_from_profiles({"c4-thread": "decode_c4_thread_kernel"}.get(kname, kname))
         roofline = {
-            "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": hbm_achieved / hbm_peak,
-            "frac_governing": MUFU_PER_EDGE_ITER * edge_it / XU_MEASURED_PEAK,   # see `governing` below
-            # ncu --set full, dram__bytes_read+write of this kernel: 523.2 B per codeword
-            # (profiles/r1_kernels_ncu_full.txt) against 518 B algorithmic
-            "traffic": n_cw * 523.2 if code.kernel_name(L.METHOD_SUMPRODUCT) == "c4-thread" else None,
-            "traffic_unit": "bytes per launch", "algorithmic_bytes": n_cw * BYTES_PER_CW,
-            "peak_source": peak_src,
-            "kernel": code.kernel_name(L.METHOD_SUMPRODUCT), "kernel_ms": kern_ms,
-            "note": "a fixed-50-iteration sum-product is bound by the SM special-function/issue "
-                    "pipes, not HBM (SURVEY 8d); `governing` is the roofline that applies",
-            "governing": {"bound": "sm_xu", "achieved": MUFU_PER_EDGE_ITER * edge_it / 1e12,
-                          "peak": XU_MEASURED_PEAK / 1e12, "unit": "T MUFU/s",
-                          "frac": MUFU_PER_EDGE_ITER * edge_it / XU_MEASURED_PEAK,
-                          "edge_iterations_per_s": edge_it,
-                          "frac_algorithmic_4xu_nominal": XU_PER_EDGE_ITER * edge_it / xu_peak_ops,
-                          "def": "executed MUFU (3 per edge-iteration: 1 ex2 + 2 lg2) x E=168 x 50 iterations per "
-                                 "codeword against the XU-pipe peak measured with tools/microbench/mufu_peak.cu; "
-                                 "frac_algorithmic_4xu_nominal uses SURVEY 8d's 4 XU ops per edge-iteration "
-                                 "against 148 SMs x 16 lanes x max SM clock"}}
+            # the roofline that governs a fixed-50-iteration sum-product: the SM special-function
+            # pipe; the HBM figure sits beside it
+            "bound": "sm_xu", "achieved": mufu / 1e12, "peak": mufu_peak / 1e12, "unit": "T MUFU/s",
+            "frac": mufu / mufu_peak,
+            "peak_source": "ldpc535_probe_pipe_peak(MUFU) on this GPU in this run: 1 ex2 : 2 lg2 mix, best of 16/32/64 "
+                           "warps per SM = %.2f lanes/clk/SM at the %.0f MHz max clock" % (mufu_peak / SM_COUNT / f_max, f_max / 1e6),
+            "def": "executed MUFU per launch = 3 per edge-iteration (1 ex2 + 2 lg2, spa_math.cuh) x E=168 x 50 "
+                   "iterations + 64 start-up ex2, per codeword, / the kernel's mean launch time",
+            "edge_iterations_per_s": edge_it,
+            "frac_algorithmic_4xu_nominal": XU_PER_EDGE_ITER * edge_it / xu_nominal,
+            "kernel": kname, "kernel_ms": kern_ms,
+            "traffic": None if per_cw is None else n_cw * per_cw, "traffic_unit": "bytes per launch",
+            "traffic_source": tsrc, "algorithmic_bytes": n_cw * BYTES_PER_CW,
+            "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_achieved / hbm_peak, "peak_source": peak_src}}
         line = {"metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -415,15 +694,28 @@ def run_gpu(args):
                         "codewords_per_gpu": e2e_cw,
                         "ms_per_step": e2e_ms / e2e_steps,
                         "api": "ldpc535_decode_batch (pinned host buffers, 3-slot stage/H2D/kernel/D2H pipeline)",
-                        "host_path": host_path, "pcie_h2d_bytes_per_step": pcie_bytes,
+                        "host_path": host_path, "host_cores_per_rank": share, "numa": numa_note,
+                        "pcie_h2d_bytes_per_step": pcie_bytes,
+                        "h2d_ceiling_gbs": h2d_ceiling,
+                        "h2d_ceiling_def": "all %d ranks copying their pinned shard at once, 128 MiB cudaMemcpyAsync "
+                                           "chunks, no kernel" % world,
+                        "frac_of_h2d_ceiling": pcie_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9 / h2d_ceiling,
                         "matches_device_path": e2e_same},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "check": {"frames_recovered": frame_ok, "frames_not_at_max_iters": bad_iters}}
+                "check": {"frames_recovered": frame_ok, "frames_not_at_max_iters": bad_iters,
+                          "inputs": "Philox4x32-10, seed %d, counter = global codeword index (shard of rank r "
+                                    "starts at r x codewords_per_gpu)" % SEED,
+                          "rank0_shard_digest": shard_digest}}
+    for p in (p1, p2, p3, p4):
+        _abi.lib().ldpc535_host_free(p)
+    if rank == 0 and world == 1 and not args.no_extras:
+        del d_bytes, d_synd, d_iters
+        line["configs"] = extra_configs(L, torch, np, code, stream, sp, d_data, d_sym, n_cw, first_frame,
+                                        mufu_peak, fp64_peak, hbm_peak, f_max)
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_per_core)
         print(json.dumps(line))
-    for p in (p1, p2, p3, p4):
-        _abi.lib().ldpc535_host_free(p)
     code.close()
     if dist:
         dist.barrier()
@@ -438,9 +730,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--codewords", type=int, default=10_000_000, help="codewords per GPU per step")
-    ap.add_argument("--cpu-per-core", type=int, default=4000, help="cpu_baseline sample per host core")
+    ap.add_argument("--cpu-per-core", type=int, default=20_000, help="cpu_baseline sample per host core (BASELINE.md 5.3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `configs` measurements (other BASELINE configs)")
     ap.add_argument("--kernel", default=None, help="force a decoder kernel family (warp/block/c4-thread)")
+    ap.add_argument("--pack-pinned", type=int, default=-1, help="e2e host path: 1 pack, 0 raw DMA, -1 from the core share")
+    ap.add_argument("--pack-threads", type=int, default=0, help="e2e packing team size (0: cores / ranks on this host)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -4,20 +4,28 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 namespace ldpc535 {
 namespace {
-void pack_range(const float *__restrict src, float *__restrict dst, size_t n)
+
+void pack_scalar(const float *__restrict src, float *__restrict dst, size_t n)
+{
+    for (size_t i = 0; i < n; i++) dst[i] = src[2 * i];
+}
+
+// 8 reals per step with non-temporal stores: the staging buffer is written once and read only
+// by the copy engine, so the read-for-ownership of every destination line is skipped.
+// Compiled for AVX2 by attribute (the rest of the file is baseline x86-64) and only called
+// after __builtin_cpu_supports("avx2") said yes.
+__attribute__((target("avx2"))) void pack_avx2(const float *__restrict src, float *__restrict dst, size_t n)
 {
     size_t i = 0;
-#if defined(__AVX2__)
-    // head up to a 32-byte boundary of dst, then 8 reals per step with non-temporal stores
-    // (the staging buffer is written once and read only by the copy engine: skip the
-    // read-for-ownership of every destination line)
     while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) { dst[i] = src[2 * i]; i++; }
     for (; i + 8 <= n; i += 8) {
         const __m256 a = _mm256_loadu_ps(src + 2 * i);        // r0 i0 r1 i1 | r2 i2 r3 i3
@@ -27,17 +35,20 @@ void pack_range(const float *__restrict src, float *__restrict dst, size_t n)
         _mm256_stream_ps(dst + i, _mm256_castpd_ps(q));
     }
     _mm_sfence();
-#endif
     for (; i < n; i++) dst[i] = src[2 * i];
 }
+
+using pack_fn = void (*)(const float *, float *, size_t);
+pack_fn pick_pack()
+{
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("avx2") ? pack_avx2 : pack_scalar;
+}
+const pack_fn g_pack = pick_pack();
+
 }  // namespace
 
-int host_sharing_ranks()
-{
-    for (const char *name : {"LOCAL_WORLD_SIZE", "WORLD_SIZE"})
-        if (const char *s = std::getenv(name)) return std::max(1, std::atoi(s));
-    return 1;
-}
+void pack_real_parts_serial(const float *src, float *dst, size_t n) { g_pack(src, dst, n); }
 
 int default_pack_threads()
 {
@@ -45,28 +56,83 @@ int default_pack_threads()
         const int v = std::atoi(s);
         if (v >= 1) return std::min(v, 64);
     }
-    // all the cores this process may run on, shared between the ranks of a multi-GPU job
-    // (one process per GPU: LOCAL_WORLD_SIZE / WORLD_SIZE as torch.distributed.run sets them)
     unsigned hc = std::thread::hardware_concurrency();
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) hc = (unsigned)CPU_COUNT(&set);
-    const unsigned ranks = (unsigned)host_sharing_ranks();
-    return (int)std::max(1u, std::min(32u, hc / ranks));
+    return (int)std::max(1u, std::min(32u, hc));
 }
 
-void pack_real_parts(const float *src, float *dst, size_t n, int threads)
+struct PackPool::Impl {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> workers;
+    // one job at a time: parts [1, parts) belong to the workers, part 0 to the caller
+    const float *src = nullptr;
+    float *dst = nullptr;
+    size_t n = 0, per = 0;
+    int parts = 0;
+    unsigned long generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    void run_part(int k) const
+    {
+        const size_t lo = std::min(n, per * (size_t)k), hi = std::min(n, per * (size_t)(k + 1));
+        if (hi > lo) g_pack(src + 2 * lo, dst + lo, hi - lo);
+    }
+
+    void worker(int id)
+    {
+        unsigned long seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            if (id < parts) {
+                lk.unlock();
+                run_part(id);
+                lk.lock();
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+};
+
+PackPool::PackPool(int threads) : impl_(new Impl), n_threads_(std::max(1, threads))
+{
+    for (int id = 1; id < n_threads_; id++) impl_->workers.emplace_back(&Impl::worker, impl_, id);
+}
+
+PackPool::~PackPool()
+{
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv_work.notify_all();
+    for (auto &t : impl_->workers) t.join();
+    delete impl_;
+}
+
+void PackPool::pack(const float *src, float *dst, size_t n)
 {
     const size_t kMinPerThread = 1u << 16;
-    int t = (int)std::min<size_t>((size_t)std::max(threads, 1), std::max<size_t>(1, n / kMinPerThread));
-    if (t <= 1) { pack_range(src, dst, n); return; }
-    std::vector<std::thread> pool;
-    pool.reserve(t - 1);
-    const size_t per = (((n + t - 1) / t) + 15) & ~(size_t)15;
-    for (int k = 1; k < t; k++) {
-        const size_t lo = std::min(n, per * k), hi = std::min(n, per * (k + 1));
-        if (hi > lo) pool.emplace_back(pack_range, src + 2 * lo, dst + lo, hi - lo);
+    const int parts = (int)std::min<size_t>((size_t)n_threads_, std::max<size_t>(1, n / kMinPerThread));
+    if (parts <= 1) { g_pack(src, dst, n); return; }
+    Impl &s = *impl_;
+    {
+        std::lock_guard<std::mutex> lk(s.mu);
+        s.src = src; s.dst = dst; s.n = n;
+        s.per = (((n + parts - 1) / parts) + 15) & ~(size_t)15;
+        s.parts = parts;
+        s.pending = parts - 1;
+        s.generation++;
     }
-    pack_range(src, dst, std::min(n, per));
-    for (auto &th : pool) th.join();
+    s.cv_work.notify_all();
+    s.run_part(0);
+    std::unique_lock<std::mutex> lk(s.mu);
+    s.cv_done.wait(lk, [&] { return s.pending == 0; });
 }
+
 }  // namespace ldpc535

@@ -7,9 +7,29 @@
 #include <cstddef>
 
 namespace ldpc535 {
-// dst[i] = src[2 * i] for i < n, split over `threads` workers (>= 1).
-void pack_real_parts(const float *src_interleaved, float *dst, size_t n, int threads);
+
+// A persistent team of worker threads (created once per handle, parked on a condition variable
+// between calls): pack() splits the span over the team and returns when every part is done.
+class PackPool
+{
+public:
+    explicit PackPool(int threads);       // threads >= 1 including the calling thread
+    ~PackPool();
+    PackPool(const PackPool &) = delete;
+    PackPool &operator=(const PackPool &) = delete;
+    int threads() const { return n_threads_; }
+    // dst[i] = src[2 * i] for i < n
+    void pack(const float *src_interleaved, float *dst, size_t n);
+
+private:
+    struct Impl;
+    Impl *impl_;
+    int n_threads_;
+};
+
+// Cores this process may run on (sched_getaffinity), capped at 32; LDPC535_PACK_THREADS overrides.
 int default_pack_threads();
-// ranks of a one-process-per-GPU job sharing this host (LOCAL_WORLD_SIZE / WORLD_SIZE), >= 1
-int host_sharing_ranks();
+// dst[i] = src[2 * i], on the calling thread (AVX2 with streaming stores when the CPU has it,
+// checked at run time; scalar otherwise)
+void pack_real_parts_serial(const float *src_interleaved, float *dst, size_t n);
 }  // namespace ldpc535

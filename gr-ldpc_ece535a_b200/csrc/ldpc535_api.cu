@@ -23,6 +23,7 @@
 #include "encode_kernels.cuh"
 #include "encode_m4r_kernel.cuh"
 #include "host_pack.h"
+#include "synth_kernels.cuh"
 #include "ldpc535_default_code.h"
 
 using namespace ldpc535;
@@ -47,17 +48,21 @@ int fail(int status, const std::string &msg)
 enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4, kHard64 = 5 };
 
 constexpr int kSlots = 3;                       // pipeline depth of the host-buffer API
-constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot
+constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot (upper bound; slots grow on demand)
+constexpr int kPackPinnedMinThreads = 12;       // pinned input is packed by the host from this many threads on
 
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    void *d_sym = nullptr;        // kChunkSymBytes
-    long long *d_off = nullptr;   // max windows
+    // staging grows on demand (a block's first general_work() with a few frames must not stall on
+    // 3 x 128 MB of cudaMalloc): capacities in bytes / windows, 0 = not allocated yet
+    size_t cap_sym = 0, cap_win = 0, cap_stage = 0;
+    void *d_sym = nullptr;        // <= kChunkSymBytes
+    long long *d_off = nullptr;   // cap_win windows
     signed char *d_pol = nullptr;
     uint8_t *d_bytes = nullptr, *d_synd = nullptr, *d_iters = nullptr;
     long long *h_off = nullptr;   // pinned, rebased offsets
-    float *h_stage = nullptr;     // pinned, kChunkSymBytes / 2: real parts packed by the host
+    float *h_stage = nullptr;     // pinned, <= kChunkSymBytes / 2: real parts packed by the host
 };
 
 }  // namespace
@@ -90,14 +95,13 @@ struct ldpc535_code {
     int forced = kAuto;
     cudaStream_t stream = nullptr;
     // host-API pipeline
-    bool slots_ready = false;
-    bool stage_ready = false;
     int pack_threads = 1;
-    int pack_pinned = 0;          // pack even when the caller's buffer is pinned: LDPC535_PACK_PINNED=1, or by
-                                  // default when this handle is the only one feeding from this host and has
-                                  // >= 8 packing threads.  Measured per 5.12 GB on B200 boxes: one GPU, 16
-                                  // cores: 8 threads 89 ms, 12+ threads 76 ms, raw PCIe 94 ms; four ranks on
-                                  // 32 cores: packing 220 ms (host memory traffic doubles), raw PCIe 101 ms.
+    int pack_pinned = 0;          // pack even when the caller's buffer is pinned.  Default: when this handle
+                                  // has >= 12 packing threads (ldpc535_code_set_host_path / LDPC535_PACK_PINNED
+                                  // override).  Measured per 5.12 GB on B200 boxes: one GPU, 16 cores: 8 threads
+                                  // 89 ms, 12+ threads 76 ms, raw PCIe 94 ms; four ranks with 8 cores each:
+                                  // packing 220 ms (host memory traffic doubles), raw PCIe 101 ms.
+    PackPool *pool = nullptr;     // persistent packing team, created on first use
     size_t max_win_per_chunk = 0;
     Slot slots[kSlots];
     uint64_t launches = 0;
@@ -145,7 +149,7 @@ int finish_create(ldpc535_code *c)
                                                std::to_string(prop.minor) + ", kernels are built for sm_100a");
     c->sm_count = prop.multiProcessorCount;
     c->pack_threads = default_pack_threads();
-    c->pack_pinned = c->pack_threads >= 8 && host_sharing_ranks() == 1;
+    c->pack_pinned = c->pack_threads >= kPackPinnedMinThreads;
     if (const char *e = getenv("LDPC535_PACK_PINNED")) c->pack_pinned = atoi(e) != 0;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -236,8 +240,10 @@ int finish_create(ldpc535_code *c)
 void release(ldpc535_code *c)
 {
     if (!c) return;
-    if (c->device < 0) { delete c; return; }
+    if (c->device < 0) { delete c->pool; delete c; return; }
     DeviceGuard g(c->device);
+    delete c->pool;
+    c->pool = nullptr;
     for (auto &s : c->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_sym); cudaFree(s.d_off); cudaFree(s.d_pol);
@@ -274,8 +280,9 @@ int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop
         // bit-flip flips a bit only when MORE than M/2 of its checks disagree (reference :464): with
         // every bit degree <= M/2 it can never flip and equals the hard decision
         const bool flipless = method == LDPC535_METHOD_BITFLIP && c->t.dv_max <= c->t.M / 2;
+        // decode_hard64_kernel keeps one 32-bit word of data bits per codeword: K <= 32, i.e. M = 32
         if ((method == LDPC535_METHOD_HARD || flipless) && c->fits_warp && c->t.N == 64 &&
-            (c->t.M & 1) == 0 && c->t.K % 8 == 0) f = kHard64;
+            c->t.M == 32) f = kHard64;
         else if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && !early_stop) f = kC4Thread;
         else if (c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT) f = kRegular;
         else if (c->fits_warp) f = kWarp;
@@ -465,35 +472,75 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
     return LDPC535_OK;
 }
 
+// Streams and events of the pipeline slots; idempotent per slot, so a failure half way leaves
+// nothing that a retry would allocate twice.
 int ensure_slots(ldpc535_code *c)
 {
-    if (c->slots_ready) return LDPC535_OK;
     const size_t frame_bytes = (size_t)c->t.N * 8;
     c->max_win_per_chunk = std::max<size_t>(1, kChunkSymBytes / frame_bytes);
-    const size_t nb = (size_t)(c->t.K + 7) / 8;
     for (auto &s : c->slots) {
-        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        CU(cudaMalloc(&s.d_sym, std::max(kChunkSymBytes, frame_bytes)));
-        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_off), c->max_win_per_chunk * sizeof(long long)));
-        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_pol), c->max_win_per_chunk));
-        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_bytes), c->max_win_per_chunk * nb));
-        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_synd), c->max_win_per_chunk));
-        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_iters), c->max_win_per_chunk));
-        CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_off), c->max_win_per_chunk * sizeof(long long)));
+        if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
-    c->slots_ready = true;
     return LDPC535_OK;
 }
 
-int ensure_stage(ldpc535_code *c)
+size_t grow_to(size_t need, size_t floor_, size_t cap)
 {
-    if (c->stage_ready) return LDPC535_OK;
-    for (auto &s : c->slots)
-        CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_stage), kChunkSymBytes / 2));
-    c->stage_ready = true;
+    size_t v = floor_;
+    while (v < need) v <<= 1;
+    return std::max(need, std::min(v, std::max(cap, need)));
+}
+
+// Make slot `s` hold sym_bytes of symbols, n_win windows and stage_bytes of pinned staging.  The
+// slot's stream must be idle (callers synchronise it before re-using the slot).  Buffers are
+// released before they are re-allocated and their pointers cleared, so an allocation failure
+// leaves the slot consistent (release() and a later retry both work).
+int slot_reserve(ldpc535_code *c, Slot &s, size_t sym_bytes, size_t n_win, size_t stage_bytes)
+{
+    const size_t frame_bytes = (size_t)c->t.N * 8;
+    const size_t nb = (size_t)(c->t.K + 7) / 8;
+    if (sym_bytes > s.cap_sym) {
+        const size_t want = grow_to(sym_bytes, (size_t)1 << 20, std::max(kChunkSymBytes, frame_bytes));
+        cudaFree(s.d_sym); s.d_sym = nullptr; s.cap_sym = 0;
+        CU(cudaMalloc(&s.d_sym, want));
+        s.cap_sym = want;
+    }
+    if (n_win > s.cap_win) {
+        const size_t want = grow_to(n_win, 4096, c->max_win_per_chunk);
+        cudaFree(s.d_off); cudaFree(s.d_pol); cudaFree(s.d_bytes); cudaFree(s.d_synd); cudaFree(s.d_iters);
+        if (s.h_off) cudaFreeHost(s.h_off);
+        s.d_off = nullptr; s.d_pol = nullptr; s.d_bytes = s.d_synd = s.d_iters = nullptr; s.h_off = nullptr;
+        s.cap_win = 0;
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_off), want * sizeof(long long)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_pol), want));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_bytes), want * nb));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_synd), want));
+        CU(cudaMalloc(reinterpret_cast<void **>(&s.d_iters), want));
+        CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_off), want * sizeof(long long)));
+        s.cap_win = want;
+    }
+    if (stage_bytes > s.cap_stage) {
+        const size_t want = grow_to(stage_bytes, (size_t)1 << 20, std::max(kChunkSymBytes / 2, frame_bytes / 2));
+        if (s.h_stage) cudaFreeHost(s.h_stage);
+        s.h_stage = nullptr; s.cap_stage = 0;
+        CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_stage), want));
+        s.cap_stage = want;
+    }
     return LDPC535_OK;
 }
+
+// On ANY exit of a host-buffer entry point -- error returns included -- wait for every slot stream:
+// async copies into the caller's output arrays and out of its (pinned) input must not outlive the
+// call, the caller is free to release those buffers as soon as it has the status.
+struct SlotDrain {
+    ldpc535_code *c;
+    ~SlotDrain()
+    {
+        for (auto &s : c->slots)
+            if (s.stream) cudaStreamSynchronize(s.stream);
+    }
+};
 
 // true when `p` is page-locked host memory the copy engine can read directly
 bool host_pointer_is_pinned(const void *p)
@@ -690,6 +737,90 @@ int ldpc535_code_host_path(const ldpc535_code *c, int *pack_pinned, int *pack_th
     return LDPC535_OK;
 }
 
+int ldpc535_code_set_host_path(ldpc535_code *c, int pack_pinned, int pack_threads)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    if (pack_threads < 0 || pack_threads > 256) return fail(LDPC535_ERR_INVALID, "pack_threads must be 0 (keep) .. 256");
+    if (pack_threads > 0 && pack_threads != c->pack_threads) {
+        c->pack_threads = pack_threads;
+        delete c->pool;                     // the team is re-created with the new size on next use
+        c->pool = nullptr;
+    }
+    c->pack_pinned = pack_pinned < 0 ? (c->pack_threads >= kPackPinnedMinThreads) : (pack_pinned != 0);
+    return LDPC535_OK;
+}
+
+// ---- measurement utilities (synth_kernels.cuh) -------------------------------------------------
+int ldpc535_synth_bytes_dev(ldpc535_code *c, uint64_t seed, uint64_t first_frame, size_t n_frames,
+                            uint8_t *d_bytes, void *stream)
+{
+    if (!c || (n_frames && !d_bytes)) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    if (!n_frames) return LDPC535_OK;
+    const int nb = (c->t.K + 7) / 8;
+    const long long total = (long long)n_frames * ((nb + 15) / 16);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
+    synth_bytes_kernel<<<grid, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
+        d_bytes, (long long)first_frame, (long long)n_frames, nb, (uint32_t)seed, (uint32_t)(seed >> 32));
+    CU(cudaGetLastError());
+    return LDPC535_OK;
+}
+
+int ldpc535_synth_awgn_dev(ldpc535_code *c, uint64_t seed, uint64_t first_frame, size_t n_frames,
+                           float sigma, float *d_sym, void *stream)
+{
+    if (!c || (n_frames && !d_sym)) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    if (c->t.N % 4 || (reinterpret_cast<uintptr_t>(d_sym) & 15))
+        return fail(LDPC535_ERR_INVALID, "N must be a multiple of 4 and d_sym 16-byte aligned");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    if (!n_frames) return LDPC535_OK;
+    const long long total = (long long)n_frames * (c->t.N / 4);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
+    synth_awgn_kernel<<<grid, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
+        reinterpret_cast<float2 *>(d_sym), (long long)first_frame, (long long)n_frames, c->t.N, sigma,
+        (uint32_t)seed, (uint32_t)(seed >> 32));
+    CU(cudaGetLastError());
+    return LDPC535_OK;
+}
+
+int ldpc535_probe_pipe_peak(ldpc535_code *c, int which, double *ops_per_s)
+{
+    if (!c || !ops_per_s || (which != LDPC535_PIPE_MUFU && which != LDPC535_PIPE_FP64))
+        return fail(LDPC535_ERR_INVALID, "bad probe arguments");
+    DeviceGuard g(c->device);
+    NEED_DEVICE(c, g);
+    void *out = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    double best = 0;
+    cudaError_t e = cudaMalloc(&out, (size_t)c->sm_count * 8 * 256 * 8);
+    if (e == cudaSuccess) e = cudaEventCreate(&a);
+    if (e == cudaSuccess) e = cudaEventCreate(&b);
+    const int iters = 4000;
+    for (int ctas = 2; ctas <= 8 && e == cudaSuccess; ctas *= 2) {          // 16, 32, 64 warps per SM
+        const int grid = c->sm_count * ctas;
+        for (int rep = 0; rep < 3 && e == cudaSuccess; rep++) {             // rep 0 warms up
+            cudaEventRecord(a, c->stream);
+            if (which == LDPC535_PIPE_MUFU) probe_mufu_kernel<<<grid, 256, 0, c->stream>>>((float *)out, iters, 0.5f);
+            else probe_fp64_kernel<<<grid, 256, 0, c->stream>>>((double *)out, iters, 0.5);
+            cudaEventRecord(b, c->stream);
+            e = cudaEventSynchronize(b);
+            float ms = 0;
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+            // per chain step: 3 MUFU, or 3 fp64-pipe instructions (2 DADD + 1 DSETP)
+            const double ops = (double)grid * 256 * iters * 8 * 3;
+            if (rep && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+        }
+    }
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("pipe probe: ") + cudaGetErrorString(e));
+    *ops_per_s = best;
+    return LDPC535_OK;
+}
+
 int ldpc535_host_alloc(size_t bytes, void **ptr)
 {
     if (!ptr) return fail(LDPC535_ERR_INVALID, "ptr is NULL");
@@ -754,6 +885,9 @@ int ldpc535_encode_batch_dev(ldpc535_code *c, const uint8_t *d_in, size_t n_fram
                              void *stream)
 {
     if (!c || (n_frames && (!d_in || !d_out))) return fail(LDPC535_ERR_INVALID, "NULL argument");
+    // the kernels read the input as 32-bit words and store symbols 16 bytes at a time
+    if ((reinterpret_cast<uintptr_t>(d_in) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return fail(LDPC535_ERR_INVALID, "device pointers must be aligned: d_in to 4 bytes, d_out to 16 bytes");
     DeviceGuard g(c->device);
     NEED_DEVICE(c, g);
     return launch_encode(c, d_in, n_frames, d_out, stream ? (cudaStream_t)stream : c->stream);
@@ -768,6 +902,10 @@ int ldpc535_decode_batch_dev(ldpc535_code *c, const float *d_sym, size_t n_sym,
     if (!c || (n_win && (!d_sym || !d_out_bytes))) return fail(LDPC535_ERR_INVALID, "NULL argument");
     if (max_iters < 1 || max_iters > 255) return fail(LDPC535_ERR_INVALID, "max_iters must be 1..255");
     if (synd_threshold < 0) return fail(LDPC535_ERR_INVALID, "synd_threshold < 0");
+    // 128-bit symbol loads, 32-bit stores of packed bytes
+    if ((reinterpret_cast<uintptr_t>(d_sym) & 15) || (reinterpret_cast<uintptr_t>(d_out_bytes) & 3) ||
+        (reinterpret_cast<uintptr_t>(d_win_offset) & 7))
+        return fail(LDPC535_ERR_INVALID, "device pointers must be aligned: d_sym to 16 bytes, d_out_bytes to 4 bytes, d_win_offset to 8 bytes");
     DeviceGuard g(c->device);
     NEED_DEVICE(c, g);
     DecodeParams p = {};
@@ -788,6 +926,7 @@ int ldpc535_encode_batch(ldpc535_code *c, const uint8_t *in, size_t n_frames, fl
     NEED_DEVICE(c, g);
     int st = ensure_slots(c);
     if (st) return st;
+    SlotDrain drain{c};
     const size_t nb = (size_t)(c->t.K + 7) / 8;
     const size_t frame_bytes = (size_t)c->t.N * 8;
     // the symbol staging buffer holds the OUTPUT here; input bytes ride in d_bytes
@@ -798,6 +937,7 @@ int ldpc535_encode_batch(ldpc535_code *c, const uint8_t *in, size_t n_frames, fl
         Slot &s = c->slots[k % kSlots];
         const size_t n = std::min(chunk, n_frames - done);
         CU(cudaStreamSynchronize(s.stream));
+        if ((st = slot_reserve(c, s, n * frame_bytes, n, 0))) return st;
         CU(cudaMemcpyAsync(s.d_bytes, in + done * nb, n * nb, cudaMemcpyHostToDevice, s.stream));
         st = launch_encode(c, s.d_bytes, n, reinterpret_cast<float *>(s.d_sym), s.stream);
         if (st) return st;
@@ -830,10 +970,15 @@ int ldpc535_decode_batch(ldpc535_code *c, const float *sym, size_t n_sym, const 
     NEED_DEVICE(c, g);
     int st = ensure_slots(c);
     if (st) return st;
+    SlotDrain drain{c};
     // Pageable input (a GNU Radio buffer) must be staged through pinned memory anyway: stage only
-    // the real parts.  Pinned input goes to the copy engine as it is unless LDPC535_PACK_PINNED=1.
+    // the real parts.  Pinned input goes to the copy engine as it is unless the handle packs pinned
+    // input too (ldpc535_code_set_host_path).
     const bool pack = n_win && (!host_pointer_is_pinned(sym) || c->pack_pinned);
-    if (pack && (st = ensure_stage(c))) return st;
+    if (pack && !c->pool) {
+        c->pool = new (std::nothrow) PackPool(c->pack_threads);
+        if (!c->pool) return fail(LDPC535_ERR_NOMEM, "out of host memory");
+    }
     const size_t max_sym = kChunkSymBytes / 8;     // symbols per staging buffer
     size_t done = 0;
     int k = 0;
@@ -856,11 +1001,14 @@ int ldpc535_decode_batch(ldpc535_code *c, const float *sym, size_t n_sym, const 
                 lo = nlo; hi = nhi; n++;
             }
             sym_lo = lo; sym_hi = hi;
-            for (size_t i = 0; i < n; i++) s.h_off[i] = (long long)((size_t)win_offset[done + i] - lo);
+        }
+        if ((st = slot_reserve(c, s, (sym_hi - sym_lo) * (pack ? 4 : 8), n, pack ? (sym_hi - sym_lo) * 4 : 0))) return st;
+        if (win_offset) {
+            for (size_t i = 0; i < n; i++) s.h_off[i] = (long long)((size_t)win_offset[done + i] - sym_lo);
             CU(cudaMemcpyAsync(s.d_off, s.h_off, n * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
         }
         if (pack) {
-            pack_real_parts(sym + sym_lo * 2, s.h_stage, sym_hi - sym_lo, c->pack_threads);
+            c->pool->pack(sym + sym_lo * 2, s.h_stage, sym_hi - sym_lo);
             CU(cudaMemcpyAsync(s.d_sym, s.h_stage, (sym_hi - sym_lo) * 4, cudaMemcpyHostToDevice, s.stream));
         } else {
             CU(cudaMemcpyAsync(s.d_sym, sym + sym_lo * 2, (sym_hi - sym_lo) * 8, cudaMemcpyHostToDevice, s.stream));
@@ -972,11 +1120,9 @@ int ldpc535_pool_create(const int32_t *H, int M, int N, const int *devices, int 
         }
         p->codes.push_back(c);
     }
-    if (n_devices > 1)                      // the handles share this host: split the packing threads,
-        for (ldpc535_code *c : p->codes) {  // leave pinned input to the copy engines
-            c->pack_threads = std::max(1, c->pack_threads / n_devices);
-            c->pack_pinned = 0;
-        }
+    if (n_devices > 1)                      // the handles share this host: split the packing threads
+        for (ldpc535_code *c : p->codes)
+            ldpc535_code_set_host_path(c, -1, std::max(1, c->pack_threads / n_devices));
     *out = p;
     return LDPC535_OK;
 }

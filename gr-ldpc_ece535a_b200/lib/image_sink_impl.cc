@@ -19,6 +19,8 @@
 #include "image_sink_impl.h"
 
 #include <gnuradio/io_signature.h>
+#include <sys/types.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <cstdlib>
@@ -73,8 +75,22 @@ void image_sink_impl::flush_file()
     d_files_written++;
     say("File written");
     if (d_display) {
-        const std::string cmd = "/usr/bin/display " + d_path + " &";
-        if (std::system(cmd.c_str()) != 0) std::fputs("image_sink: could not start the viewer\n", stderr);
+        // the reference runs `/usr/bin/display result.bmp &` through system() (:68); the path can
+        // come from the environment here, so no shell is involved: double fork + execl, the
+        // viewer is re-parented to init and never becomes a zombie of the flowgraph
+        const pid_t pid = fork();
+        if (pid == 0) {
+            if (fork() == 0) {
+                execl("/usr/bin/display", "display", d_path.c_str(), (char *)NULL);
+                _exit(127);
+            }
+            _exit(0);
+        } else if (pid > 0) {
+            int status = 0;
+            waitpid(pid, &status, 0);
+        } else {
+            std::fputs("image_sink: could not start the viewer\n", stderr);
+        }
     }
 }
 

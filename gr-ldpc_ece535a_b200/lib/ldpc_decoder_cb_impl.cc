@@ -47,6 +47,7 @@ int device_from_env()
 }
 // How far the batcher speculates on a miss.
 const long kTrackBatch = 1 << 16;   // frames at the frame stride
+const size_t kMaxEventLog = 65536;  // most recent sync events kept in d_events
 const long kSearchBatch = 2048;     // offsets, each in both polarities (a failed search costs one GPU call per 2048 slides;
                                     // a GPU call is ~0.15 ms of latency whatever its size, 4096 windows are ~10 us of kernel)
 }  // namespace
@@ -72,11 +73,11 @@ ldpc_decoder_cb_impl::ldpc_decoder_cb_impl(const int method)
     d_nbytes = K / 8;
     d_threshold = d_M / 8;
 
-    // same console line as the reference constructor (:108-116)
-    if (d_method == 3) say("Decoding method: Hard Decision");
-    else if (d_method == 2) say("Decoding method: Bit Flipping");
-    else if (d_method == 1) say("Decoding method: Sum Product");
-    else say("Decoding method: Log Domain Simple");
+    // the console line of the reference constructor, verbatim (:108-116)
+    if (d_method == 3) say("Method: Hard");
+    else if (d_method == 2) say("Method: BitFlip");
+    else if (d_method == 1) say("Method: SumProduct");
+    else say("Method: LogDomain");
 
     // One output byte needs 16 input symbols; whole frames only.  Hints for the scheduler's
     // buffer sizing, they do not change what is produced.
@@ -170,6 +171,10 @@ int ldpc_decoder_cb_impl::general_work(int noutput_items, gr_vector_int &ninput_
     try {
         produced = d_sync.run(*this, d_ninput, noutput_items, d_N, d_nbytes, d_threshold, out,
                               &consumed, [this](int ev) {
+                                  // bounded log for tests / monitoring: a flowgraph that never
+                                  // reads it must not grow without limit
+                                  if (d_events.size() >= kMaxEventLog)
+                                      d_events.erase(d_events.begin(), d_events.begin() + kMaxEventLog / 2);
                                   d_events.push_back(ev);
                                   if (ev == EV_IN_SYNC) say("IN SYNC");
                                   else if (ev == EV_IN_SYNC_INVERTED) say("IN SYNC; PHASE INVERTED");

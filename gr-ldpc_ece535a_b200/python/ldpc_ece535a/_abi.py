@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("LDPC535_LIB") or os.path.normpath(os.path.join(_PKG, 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_SINGULAR, ERR_UNSUPPORTED, ERR_NOMEM = range(7)
 
 METHOD_LOGDOMAIN, METHOD_SUMPRODUCT, METHOD_BITFLIP, METHOD_HARD = 0, 1, 2, 3
+PIPE_MUFU, PIPE_FP64 = 0, 1
 
 # every symbol include/ldpc535.h declares: name -> (restype, argtypes)
 _vp, _i, _sz, _u64 = C.c_void_p, C.c_int, C.c_size_t, C.c_uint64
@@ -40,6 +41,10 @@ SYMBOLS = {
     "ldpc535_pool_decode_batch": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _vp]),
     "ldpc535_pool_encode_batch": (_i, [_vp, _vp, _sz, _vp]),
     "ldpc535_code_host_path": (_i, [_vp, _pi, _pi]),
+    "ldpc535_code_set_host_path": (_i, [_vp, _i, _i]),
+    "ldpc535_synth_bytes_dev": (_i, [_vp, _u64, _u64, _sz, _vp, _vp]),
+    "ldpc535_synth_awgn_dev": (_i, [_vp, _u64, _u64, _sz, C.c_float, _vp, _vp]),
+    "ldpc535_probe_pipe_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),
     "ldpc535_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "ldpc535_host_free": (_i, [_vp]),
     "ldpc535_encode_batch": (_i, [_vp, _vp, _sz, _vp]),

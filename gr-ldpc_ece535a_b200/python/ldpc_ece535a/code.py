@@ -90,6 +90,10 @@ class Code:
         check(lib().ldpc535_code_host_path(self._h, a, b), "host_path")
         return {"pack_pinned": bool(a.value), "pack_threads": b.value}
 
+    def set_host_path(self, pack_pinned=-1, pack_threads=0):
+        """pack_threads >= 1 (0 keeps it); pack_pinned 0 / 1, or -1 to derive it from the team size."""
+        check(lib().ldpc535_code_set_host_path(self._h, int(pack_pinned), int(pack_threads)), "set_host_path")
+
     def launch_count(self):
         return int(lib().ldpc535_launch_count(self._h))
 
@@ -162,6 +166,20 @@ class Code:
                                              int(n_win), int(method), int(max_iters),
                                              int(bool(early_stop)), thr, d_out_bytes, d_out_synd,
                                              d_out_iters, stream), "decode_batch_dev")
+
+    def synth_bytes_dev(self, seed, first_frame, n_frames, d_bytes, stream=None):
+        check(lib().ldpc535_synth_bytes_dev(self._h, int(seed), int(first_frame), int(n_frames), d_bytes, stream),
+              "synth_bytes_dev")
+
+    def synth_awgn_dev(self, seed, first_frame, n_frames, sigma, d_sym, stream=None):
+        check(lib().ldpc535_synth_awgn_dev(self._h, int(seed), int(first_frame), int(n_frames), float(sigma),
+                                           d_sym, stream), "synth_awgn_dev")
+
+    def probe_pipe_peak(self, which):
+        """Measured thread-level ops/s of an SM pipe (_abi.PIPE_MUFU / PIPE_FP64)."""
+        v = C.c_double()
+        check(lib().ldpc535_probe_pipe_peak(self._h, int(which), C.byref(v)), "probe_pipe_peak")
+        return v.value
 
     def sync(self, stream=None):
         check(lib().ldpc535_stream_sync(self._h, stream), "stream_sync")

@@ -159,7 +159,10 @@ LDPC535_API int ldpc535_decode_batch(ldpc535_code *code, const float *sym, size_
 /* ---- device-resident API (benchmarks, pipelines that already live in HBM) - */
 /* All pointers are device pointers on the handle's device.  `stream` is a
  * cudaStream_t (NULL = the handle's own stream).  Asynchronous: returns after
- * enqueueing; use ldpc535_stream_sync or your own stream/event calls. */
+ * enqueueing; use ldpc535_stream_sync or your own stream/event calls.
+ * Alignment (cudaMalloc'ed buffers satisfy all of it; a misaligned pointer is refused with
+ * LDPC535_ERR_INVALID instead of faulting on the device): d_sym and the encoder's d_out to
+ * 16 bytes, d_out_bytes and the encoder's d_in to 4 bytes, d_win_offset to 8 bytes. */
 LDPC535_API int ldpc535_encode_batch_dev(ldpc535_code *code, const uint8_t *d_in,
                                          size_t n_frames, float *d_out, void *stream);
 LDPC535_API int ldpc535_decode_batch_dev(ldpc535_code *code, const float *d_sym, size_t n_sym,
@@ -198,13 +201,17 @@ LDPC535_API int ldpc535_decode_debug(ldpc535_code *code, const float *sym, size_
 LDPC535_API int ldpc535_code_set_kernel(ldpc535_code *code, const char *kernel);
 
 /* How ldpc535_decode_batch moves host symbols to the device.  Pageable input is always staged
- * through pinned memory by `pack_threads` host threads that copy only the REAL parts (the
- * decoder never reads the imaginary ones), halving the PCIe bytes; *pack_pinned != 0 means
- * pinned input is packed the same way instead of being handed to the copy engine as it is
- * (default when >= 8 threads are available and no other rank / pool handle feeds from the same
- * host -- with several GPUs the host memory traffic of packing costs more than the PCIe bytes
- * it saves; LDPC535_PACK_PINNED / LDPC535_PACK_THREADS override). */
+ * through pinned memory by a persistent team of `pack_threads` host threads that copy only the
+ * REAL parts (the decoder never reads the imaginary ones), halving the PCIe bytes; *pack_pinned
+ * != 0 means pinned input is packed the same way instead of being handed to the copy engine as
+ * it is.  Defaults: pack_threads = the cores this process may run on (at most 32), pack_pinned =
+ * (pack_threads >= 12) -- with fewer threads per GPU the host memory traffic of packing costs more
+ * than the PCIe bytes it saves. */
 LDPC535_API int ldpc535_code_host_path(const ldpc535_code *code, int *pack_pinned, int *pack_threads);
+/* Override them, e.g. from a launcher that runs one process per GPU and knows how many host cores
+ * each process gets: pack_threads >= 1 (0 keeps the current team size); pack_pinned 0 / 1, or -1
+ * to re-derive it from the team size.  The library itself reads no launcher environment. */
+LDPC535_API int ldpc535_code_set_host_path(ldpc535_code *code, int pack_pinned, int pack_threads);
 
 /* ---- several GPUs from one host process -------------------------------------- */
 /* Codewords are independent, so a batch is cut into contiguous shards, one per device, each
@@ -225,6 +232,23 @@ LDPC535_API int ldpc535_pool_decode_batch(ldpc535_pool *pool, const float *sym, 
                                           uint8_t *out_iters);
 LDPC535_API int ldpc535_pool_encode_batch(ldpc535_pool *pool, const uint8_t *in, size_t n_frames,
                                           float *out);
+
+/* ---- measurement utilities (no reference counterpart; used by bench.py and the tests) --------- */
+/* Counter-based synthetic inputs: Philox4x32-10 keyed by `seed`, counter = GLOBAL frame index
+ * first_frame + f, so any shard of a multi-GPU run holds the frames a one-GPU run has at the same
+ * indices.  synth_bytes: n_frames * ceil(K/8) uniform data bytes.  synth_awgn: adds sigma * N(0,1)
+ * to the REAL part of each of the n_frames * N symbols in d_sym (the reference simulator's AWGN
+ * convention is sigma^2 = 10^(-EbN0_dB/10), apps/ldpc_lapack.cpp:635-642).  Asynchronous. */
+LDPC535_API int ldpc535_synth_bytes_dev(ldpc535_code *code, uint64_t seed, uint64_t first_frame,
+                                        size_t n_frames, uint8_t *d_bytes, void *stream);
+LDPC535_API int ldpc535_synth_awgn_dev(ldpc535_code *code, uint64_t seed, uint64_t first_frame,
+                                       size_t n_frames, float sigma, float *d_sym, void *stream);
+/* Measured ceiling of an SM pipe on the handle's device, in thread-level operations per second
+ * (synchronous, ~50 ms): the denominators of the compute rooflines bench.py reports.
+ * LDPC535_PIPE_MUFU: special-function pipe, the sum-product mix of 1 ex2 : 2 lg2;
+ * LDPC535_PIPE_FP64: fp64 pipe, min-sum's mix of 2 DADD : 1 DSETP. */
+enum { LDPC535_PIPE_MUFU = 0, LDPC535_PIPE_FP64 = 1 };
+LDPC535_API int ldpc535_probe_pipe_peak(ldpc535_code *code, int which, double *ops_per_s);
 
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 LDPC535_API uint64_t ldpc535_launch_count(const ldpc535_code *code);

@@ -159,6 +159,27 @@ def test_c8k_decisions_match_reference_build(monkeypatch, variant):
     code.close()
 
 
+@pytest.mark.parametrize("kernel", ["regular-rt", "regular-1024", "block"])
+def test_c8k_decisions_match_reference_build_50_iterations(monkeypatch, kernel):
+    """The reference's own decodeSumProductSoft run to its exit or to 50 iterations on 36 frames at
+    1.0 / 1.5 / 2.0 dB -- 12 of them never converge (tools/gen_ref_golden_c8k_50it.py ->
+    ref_build_c8k_50it.npz): data bytes of the decision and checkFrame(v, M/8) identical for every
+    CTA-per-codeword kernel; iteration counts equal the restatement's (the reference does not
+    return its own)."""
+    g = np.load(os.path.join(GOLD, "ref_build_c8k_50it.npz"))
+    monkeypatch.setenv("LDPC535_REGULAR_VARIANT", "0" if kernel == "regular-1024" else "1")
+    rp, ci, M, N = L.codes.regular_code(8192, 3, 6, int(g["seed"]))
+    code = L.Code((rp, ci, M, N), device=0)
+    code.set_kernel("block" if kernel == "block" else "regular")
+    want = np.unpackbits(g["spa50_vhat"], axis=1)[:, :N]
+    b, sy, it = code.decode(g["rx"].astype(np.complex64), method=1, max_iters=50, early_stop=True)
+    code.close()
+    assert np.array_equal(b, np.packbits(want[:, M:], axis=1))
+    # one byte per window: the C ABI caps the threshold at 253, so the weight saturates at 254
+    assert np.array_equal(sy.astype(np.int32), np.minimum(g["spa50_synd"], 254))
+    assert np.array_equal(it.astype(np.int32), g["iters_oracle"])
+
+
 # ---------------------------------------------------------------------------------------------
 # live: the prebuilt reference library on the GPU box
 # ---------------------------------------------------------------------------------------------

@@ -200,6 +200,25 @@ def test_c8k_sparse_oracle_matches_reference_build(g8k, c8k_host, name, method, 
         assert np.array_equal(np.packbits(vhat.astype(np.uint8)), g8k[name + "_vhat"][f]), (name, f)
 
 
+def test_c8k_sparse_oracle_matches_reference_build_50_iterations(c8k_host):
+    """36 frames at 1.0 / 1.5 / 2.0 dB through the reference's decodeSumProductSoft to its exit or
+    to 50 iterations (tools/gen_ref_golden_c8k_50it.py; 12 frames never converge, the others take
+    14-45 iterations): the sparse restatement gives the same 8192 decisions on every one, the
+    same saturating syndrome weight, and stops at the stored iteration counts."""
+    g = np.load(os.path.join(GOLD, "ref_build_c8k_50it.npz"))
+    code, _ = c8k_host
+    row_ptr, col_idx = code.h_csr()
+    tables = util.sparse_tables(row_ptr, col_idx, code.M, code.N)
+    vhat, iters = util.oracle_spa_sparse_batch(g["rx"], tables, code.M, code.N, 50, True)
+    assert np.array_equal(np.packbits(vhat, axis=1), g["spa50_vhat"])
+    assert np.array_equal(iters, g["iters_oracle"])
+    synd = util.syndrome_weights(vhat, row_ptr, col_idx, code.M)
+    # checkFrame(v, M/8) stops counting at M/8 + 1 (lib/ldpc_decoder_cb_impl.cc:236-253)
+    assert np.array_equal(np.minimum(synd, code.M // 8 + 1), g["spa50_synd"])
+    assert (iters[:12] == 50).all() and (synd[:12] > 0).all()      # the 1.0 dB frames do not converge
+    assert (synd[iters < 50] == 0).all()
+
+
 # ---------------------------------------------------------------------------------------------
 # live: the library itself
 # ---------------------------------------------------------------------------------------------

@@ -63,3 +63,41 @@ def oracle_spa_batch(sym, Hp, iterations, early_stop, threshold=None):
 def csr_to_edges(row_ptr, col_idx):
     rows = np.repeat(np.arange(len(row_ptr) - 1), np.diff(row_ptr))
     return rows, np.asarray(col_idx)
+
+
+def sparse_tables(row_ptr, col_idx, M, N):
+    """CSR + per-column edge lists in the form oracle.decode_spa_sparse takes."""
+    rows = np.repeat(np.arange(M), np.diff(row_ptr))
+    order = np.lexsort((rows, col_idx))
+    col_ptr = np.zeros(N + 1, np.int32)
+    np.add.at(col_ptr, np.asarray(col_idx) + 1, 1)
+    return (np.asarray(row_ptr, np.int32), np.asarray(col_idx, np.int32),
+            np.cumsum(col_ptr).astype(np.int32), order.astype(np.int32))
+
+
+def oracle_spa_sparse_batch(rx, tables, M, N, iterations, early_stop, threads=None):
+    """Sparse restatement over a batch of real-valued frames, one frame per task on a thread pool
+    (ctypes drops the GIL).  -> (vhat (n, N) uint8, iters (n,) int32)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    rx = np.asarray(rx)
+    n = rx.shape[0]
+    vhat = np.zeros((n, N), np.uint8)
+    iters = np.zeros(n, np.int32)
+
+    def one(f):
+        v, run = O.decode_spa_sparse(rx[f], tables, M, N, iterations, early_stop)
+        vhat[f] = v
+        iters[f] = run
+
+    with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(one, range(n)))
+    return vhat, iters
+
+
+def syndrome_weights(vhat, row_ptr, col_idx, M):
+    """Number of unsatisfied checks of every row of vhat (n, N)."""
+    rows = np.repeat(np.arange(M), np.diff(row_ptr))
+    s = np.zeros((vhat.shape[0], M), np.int64)
+    np.add.at(s.T, rows, vhat[:, col_idx].T.astype(np.int64))
+    return (s & 1).sum(1)
