@@ -374,7 +374,7 @@ def extra_configs(L, torch, np, c4, stream, sp, d_data, d_sym, n_cw, first_frame
             ms = time_launches(stream, one, 3, 2)
             it_sum = float(d_iters.sum(dtype=torch.float64).item())
             row = {"method": name, "ebn0_db": ebn0, "max_iters": 5, "early_stop": 1, "codewords": n_cw,
-                   "kernel": c4.kernel_name(method), "ms": ms, "gbit_s": n_cw * K_INFO / ms / 1e6,
+                   "kernel": c4.kernel_for(method, True, n_cw), "ms": ms, "gbit_s": n_cw * K_INFO / ms / 1e6,
                    "mean_iters": it_sum / n_cw,
                    "frames_recovered": float((d_bytes == d_data).all(dim=1).float().mean().item())}
             eit = it_sum * E_EDGES / (ms * 1e-3)

@@ -181,12 +181,12 @@ decode_c4_thread_kernel(const DecodeParams p)
 #pragma unroll
                 for (int i = 0; i < kN / 4; i++) {
                     const float4 v = __ldg(s4 + i);
-                    r[4 * i] = npol * v.x; r[4 * i + 1] = npol * v.y;
-                    r[4 * i + 2] = npol * v.z; r[4 * i + 3] = npol * v.w;
+                    r[4 * i] = __fmul_rn(npol, v.x); r[4 * i + 1] = __fmul_rn(npol, v.y);
+                    r[4 * i + 2] = __fmul_rn(npol, v.z); r[4 * i + 3] = __fmul_rn(npol, v.w);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < kN; i++) r[i] = npol * __ldg(s + i);
+                for (int i = 0; i < kN; i++) r[i] = __fmul_rn(npol, __ldg(s + i));
             }
         } else if (ok) {
             const float2 *s = p.sym + off;
@@ -195,12 +195,12 @@ decode_c4_thread_kernel(const DecodeParams p)
 #pragma unroll
                 for (int i = 0; i < kN / 2; i++) {
                     const float4 v = __ldg(s4 + i);
-                    r[2 * i] = npol * v.x;
-                    r[2 * i + 1] = npol * v.z;
+                    r[2 * i] = __fmul_rn(npol, v.x);
+                    r[2 * i + 1] = __fmul_rn(npol, v.z);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < kN; i++) r[i] = npol * __ldg(&s[i].x);
+                for (int i = 0; i < kN; i++) r[i] = __fmul_rn(npol, __ldg(&s[i].x));
             }
         } else {
 #pragma unroll

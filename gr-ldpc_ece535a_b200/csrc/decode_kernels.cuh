@@ -93,8 +93,10 @@ __device__ __forceinline__ uint8_t pack_msb_first(uint32_t bits8)
 // ---------------------------------------------------------------------------------
 // warp per codeword
 // ---------------------------------------------------------------------------------
+// 8 CTAs (32 warps) per SM for the sparse instantiation; the dense one (check degree <= 16, bit degree
+// <= 8) holds 16 + 2 x 8 messages per lane and spilled ~500 bytes at 64 registers: 4 CTAs per SM there.
 template <int METHOD, int DC, int DV, bool DEBUG>
-__global__ void __launch_bounds__(kWarpKernelThreads, WARP_MIN_BLOCKS)
+__global__ void __launch_bounds__(kWarpKernelThreads, (DC <= 6 ? WARP_MIN_BLOCKS : WARP_MIN_BLOCKS / 2))
 decode_warp_kernel(const DecodeParams p)
 {
     using T = msg_t<METHOD>;
@@ -162,7 +164,7 @@ decode_warp_kernel(const DecodeParams p)
 #pragma unroll
         for (int t = 0; t < 2; t++) {
             const int v = lane + 32 * t;
-            r[t] = (T)((ok && v < N) ? (-pol * kIn) * load_re(p, off + v) : 0.f);
+            r[t] = (T)((ok && v < N) ? __fmul_rn(-pol * kIn, load_re(p, off + v)) : 0.f);
         }
         float rk[2][DV];                               // r on a real edge of the bit, 0 on an unused slot
 #pragma unroll
@@ -366,7 +368,7 @@ decode_block_kernel(const DecodeParams p)
         constexpr float kIn = (METHOD == kMethodSpa) ? kSpaScale : 1.f;
         constexpr float kOut = (METHOD == kMethodSpa) ? kSpaUnscale : 1.f;
         __syncthreads();                                   // previous window fully drained
-        for (int i = tid; i < N; i += nt) r[i] = ok ? (-pol * kIn) * load_re(p, off + i) : 0.f;
+        for (int i = tid; i < N; i += nt) r[i] = ok ? __fmul_rn(-pol * kIn, load_re(p, off + i)) : 0.f;
         if (tid == 0) red[0] = 0;
         __syncthreads();
 

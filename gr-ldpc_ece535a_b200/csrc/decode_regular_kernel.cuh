@@ -72,7 +72,7 @@ decode_regular_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row
         const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
         const bool ok = off >= 0 && off + N <= p.n_sym;
         __syncthreads();                                   // previous window fully drained
-        for (int i = tid; i < N; i += nt) r[i] = ok ? (-pol * kSpaScale) * load_re(p, off + i) : 0.f;
+        for (int i = tid; i < N; i += nt) r[i] = ok ? __fmul_rn(-pol * kSpaScale, load_re(p, off + i)) : 0.f;
         if (tid == 0) red[0] = 0;
         __syncthreads();
         // M_ji = r_i on every edge, stored as t = copysign(2^-|M|, M), no tags yet
@@ -232,7 +232,7 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
         const bool ok = off >= 0 && off + N <= p.n_sym;
         float r[BQ];
 #pragma unroll
-        for (int q = 0; q < BQ; q++) r[q] = ok ? (-pol * kSpaScale) * load_re(p, off + q * NT + tid) : 0.f;
+        for (int q = 0; q < BQ; q++) r[q] = ok ? __fmul_rn(-pol * kSpaScale, load_re(p, off + q * NT + tid)) : 0.f;
         __syncthreads();                                   // previous window fully drained; red[1] visible
         const long long w_next = (long long)(unsigned int)red[1];
         // pull the next window of this CTA towards L2 while this one iterates (one 128-byte line per thread)

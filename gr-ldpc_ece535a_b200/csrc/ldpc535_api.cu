@@ -18,6 +18,7 @@
 #include "code_tables.h"
 #include "decode_kernels.cuh"
 #include "decode_c4_kernel.cuh"
+#include "decode_c4_refill_kernel.cuh"
 #include "decode_regular_kernel.cuh"
 #include "decode_hard_kernel.cuh"
 #include "encode_kernels.cuh"
@@ -45,7 +46,7 @@ int fail(int status, const std::string &msg)
             return fail(LDPC535_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4, kHard64 = 5 };
+enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4, kHard64 = 5, kC4Refill = 6 };
 
 constexpr int kSlots = 3;                       // pipeline depth of the host-buffer API
 constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot (upper bound; slots grow on demand)
@@ -81,6 +82,7 @@ struct ldpc535_code {
     uint16_t *d_var_row4 = nullptr;   // [N][4] message addresses of a bit (regular codes, dv <= 4)
     unsigned int *d_cursor = nullptr; // window cursors of the register-table kernel (one per launch in flight, round-robin)
     unsigned int cursor_launch = 0;
+    int c4_refill_min = 1;            // "c4-refill": lanes of a warp that must be waiting before its slots are refilled
     bool fits_regular = false;
     int regular_variant = 1;          // 1: 512-thread register-table kernel (fixed sizes), 0: 1024-thread kernel
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
@@ -231,6 +233,7 @@ int finish_create(ldpc535_code *c)
     nt = std::min(1024, ((nt + 31) / 32) * 32);
     c->block_threads = std::max(nt, 64);
     if (const char *e = getenv("LDPC535_REGULAR_VARIANT")) c->regular_variant = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("LDPC535_C4_REFILL_MIN")) c->c4_refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("LDPC535_BLOCK_THREADS")) c->block_threads = std::max(64, std::min(1024, atoi(e) / 32 * 32));
     if (!c->fits_warp && !c->fits_block)
         return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the shared-memory resident decoder");
@@ -265,6 +268,7 @@ int family_from_name(const char *name, int *out)
     if (!strcmp(name, "warp")) { *out = kWarp; return 0; }
     if (!strcmp(name, "block")) { *out = kBlock; return 0; }
     if (!strcmp(name, "c4-thread")) { *out = kC4Thread; return 0; }
+    if (!strcmp(name, "c4-refill")) { *out = kC4Refill; return 0; }
     if (!strcmp(name, "regular")) { *out = kRegular; return 0; }
     return 1;
 }
@@ -273,7 +277,7 @@ int family_from_name(const char *name, int *out)
 // early stop its time does not drop when frames converge early; the warp-per-codeword kernel
 // stops each codeword on its own (measured on B200, 5 iterations max: equal at 2 dB, warp kernel
 // 1.1x / 1.5x / 2x faster at 4 / 6 / 8 dB; profiles/r1_microbench.txt).
-int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop = 0)
+int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop = 0, long long n_win = 0)
 {
     int f = forced;
     if (f == kAuto) {
@@ -283,12 +287,22 @@ int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop
         // decode_hard64_kernel keeps one 32-bit word of data bits per codeword: K <= 32, i.e. M = 32
         if ((method == LDPC535_METHOD_HARD || flipless) && c->fits_warp && c->t.N == 64 &&
             c->t.M == 32) f = kHard64;
+        // Thread per codeword at fixed iterations.  With early stop: warp per codeword.  The persistent-slot
+        // thread kernel (decode_c4_refill_kernel, "c4-refill") is opt-in: measured against the warp kernel
+        // at 5 iterations max it is 1.02x / 0.89x / 1.00x / 1.23x as fast at Eb/N0 = 2 / 4 / 6 / 8 dB and
+        // 0.77x at 50 iterations max, 2 dB (profiles/r2_refill_sweep.txt) -- a win only on clean channels.
         else if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && !early_stop) f = kC4Thread;
         else if (c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT) f = kRegular;
         else if (c->fits_warp) f = kWarp;
         else f = kBlock;
     }
     if (f == kC4Thread && !(c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
+    if (f == kC4Refill) {
+        if (!(c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
+        // early stop and batches that fill the GPU twice over (and fit its 32-bit offsets); else its siblings
+        if (!early_stop) f = kC4Thread;
+        else if (n_win < (long long)c->sm_count * c4::kRfThreads * 2 || n_win >= (1ll << 26)) f = kWarp;
+    }
     if (f == kRegular && !(c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
     if (f == kWarp && !c->fits_warp) return -1;
     if (f == kBlock && !c->fits_block) return -1;
@@ -363,7 +377,7 @@ cudaError_t launch_generic(const ldpc535_code *c, int family, int method, bool d
 int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParams p, cudaStream_t st)
 {
     method = norm_method(method);
-    int family = resolve_family(c, forced, method, p.early_stop);
+    int family = resolve_family(c, forced, method, p.early_stop, p.n_win);
     if (family < 0) return fail(LDPC535_ERR_UNSUPPORTED, "kernel family not available for this code/method");
     if (p.n_win == 0) return LDPC535_OK;
     p.M = c->t.M; p.N = c->t.N; p.K = c->t.K; p.E = c->t.E;
@@ -413,7 +427,14 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
                 e = cudaGetLastError();
             }
         }
-    } else if (family == kC4Thread) e = launch_c4_thread(p, dbg, c->sm_count, st);
+    } else if (family == kC4Refill && !dbg && p.n_sym < (1ll << 32)) {
+        if (!c->d_cursor && cudaMalloc(reinterpret_cast<void **>(&c->d_cursor), 64 * sizeof(unsigned int)) != cudaSuccess)
+            return fail(LDPC535_ERR_CUDA, "cursor allocation");
+        unsigned int *cursor = c->d_cursor + (c->cursor_launch++ & 63u);      // zeroed on the stream just before its launch
+        if ((e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st)) != cudaSuccess)
+            return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
+        e = launch_c4_refill(p, cursor, c->c4_refill_min, c->sm_count, st);
+    } else if (family == kC4Thread || family == kC4Refill) e = launch_c4_thread(p, dbg, c->sm_count, st);
     else if (c->dc_t == 6) e = launch_generic<6, 3>(c, family, method, dbg, p, st);
     else e = launch_generic<16, 8>(c, family, method, dbg, p, st);
     if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("decode launch: ") + cudaGetErrorString(e));
@@ -708,6 +729,23 @@ const char *ldpc535_code_kernel_name(const ldpc535_code *c, int method)
     case kWarp: return "warp";
     case kBlock: return "block";
     case kC4Thread: return "c4-thread";
+    case kC4Refill: return "c4-refill";
+    case kRegular: return "regular";
+    case kHard64: return "hard64";
+    default: return "unsupported";
+    }
+}
+
+const char *ldpc535_code_kernel_for(const ldpc535_code *c, int method, int early_stop, size_t n_win)
+{
+    if (!c) return "";
+    const int m = norm_method(method);
+    const int f = resolve_family(c, c->forced, m, early_stop ? 1 : 0, (long long)n_win);
+    switch (f) {
+    case kC4Refill: return "c4-refill";
+    case kWarp: return "warp";
+    case kBlock: return "block";
+    case kC4Thread: return "c4-thread";
     case kRegular: return "regular";
     case kHard64: return "hard64";
     default: return "unsupported";
@@ -721,7 +759,7 @@ int ldpc535_code_set_kernel(ldpc535_code *c, const char *kernel)
     if (family_from_name(kernel, &f)) return fail(LDPC535_ERR_INVALID, "unknown kernel family");
     if (f == kWarp && !c->fits_warp) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the warp kernel");
     if (f == kBlock && !c->fits_block) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the block kernel");
-    if (f == kC4Thread && !c->is_c4) return fail(LDPC535_ERR_UNSUPPORTED, "not the shipped 32x64 code");
+    if ((f == kC4Thread || f == kC4Refill) && !c->is_c4) return fail(LDPC535_ERR_UNSUPPORTED, "not the shipped 32x64 code");
     if (f == kRegular && !c->fits_regular) return fail(LDPC535_ERR_UNSUPPORTED, "not a (3,6)-regular code that fits shared memory");
     c->forced = f;
     return LDPC535_OK;

@@ -76,20 +76,28 @@ __device__ __forceinline__ uint32_t check_node_spa(float (&m)[DC])
     // The first step of each recurrence and the two end combinations below are written out
     // (fma(e, 0, 1) = 1, fma(e, 1, 0) = e: exact), so a check evaluated with its exact degree
     // and the same check padded with e = 0 slots give the same bits.
+    //
+    // Every operation is spelled with a round-to-nearest intrinsic (__fmaf_rn / __fmul_rn / __fsub_rn),
+    // which the compiler may neither fuse nor split.  With plain operators it did: in an instantiation
+    // whose degree is a compile-time constant it knows se[s] == 1 for the last-but-one slot, rewrites
+    // fma(po, 1, pe * so) as po + pe * so and contracts that into ONE fma(pe, so, po) -- a single
+    // rounding where the padded instantiation rounds twice.  One ulp in od there moved a message by
+    // 5e-6 relative and, on 1 frame in 10^7 at 2 dB, a hard decision (found by diffing the kernel
+    // families on 10 M frames, tools/diff_kernels.py).
     float pe[DC], po[DC], se[DC], so[DC];
     pe[0] = 1.f; po[0] = 0.f;
     if constexpr (DC > 1) { pe[1] = 1.f; po[1] = e[0]; }
 #pragma unroll
     for (int s = 2; s < DC; s++) {
-        pe[s] = fmaf(e[s - 1], po[s - 1], pe[s - 1]);
-        po[s] = fmaf(e[s - 1], pe[s - 1], po[s - 1]);
+        pe[s] = __fmaf_rn(e[s - 1], po[s - 1], pe[s - 1]);
+        po[s] = __fmaf_rn(e[s - 1], pe[s - 1], po[s - 1]);
     }
     se[DC - 1] = 1.f; so[DC - 1] = 0.f;
     if constexpr (DC > 1) { se[DC - 2] = 1.f; so[DC - 2] = e[DC - 1]; }
 #pragma unroll
     for (int s = DC - 3; s >= 0; s--) {
-        se[s] = fmaf(e[s + 1], so[s + 1], se[s + 1]);
-        so[s] = fmaf(e[s + 1], se[s + 1], so[s + 1]);
+        se[s] = __fmaf_rn(e[s + 1], so[s + 1], se[s + 1]);
+        so[s] = __fmaf_rn(e[s + 1], se[s + 1], so[s + 1]);
     }
     const uint32_t base = sx & 0x80000000u;                 // sign of the product over all inputs
 #pragma unroll
@@ -98,10 +106,10 @@ __device__ __forceinline__ uint32_t check_node_spa(float (&m)[DC])
         if (s == 0) { ev = se[0]; od = so[0]; }
         else if (s == DC - 1) { ev = pe[s]; od = po[s]; }
         else {
-            ev = fmaf(po[s], so[s], pe[s] * se[s]);
-            od = fmaf(po[s], se[s], pe[s] * so[s]);
+            ev = __fmaf_rn(po[s], so[s], __fmul_rn(pe[s], se[s]));
+            od = __fmaf_rn(po[s], se[s], __fmul_rn(pe[s], so[s]));
         }
-        const float mag = lg2_approx(ev) - lg2_approx(od);
+        const float mag = __fsub_rn(lg2_approx(ev), lg2_approx(od));
         // mag >= 0 (even >= odd): attach sign(all inputs) ^ sign(own input)
         m[s] = __uint_as_float(__float_as_uint(mag) ^ ((__float_as_uint(m[s]) & 0x80000000u) ^ base));
     }
@@ -149,20 +157,20 @@ __device__ __forceinline__ float var_node_spa_rk(float (&x)[DV], const float (&r
 {
     float q[DV], pre[DV], suf[DV];
 #pragma unroll
-    for (int k = 0; k < DV; k++) q[k] = x[k] + rk[k];
+    for (int k = 0; k < DV; k++) q[k] = __fadd_rn(x[k], rk[k]);      // never fused with the product that made r
     pre[0] = q[0];
 #pragma unroll
-    for (int k = 1; k < DV; k++) pre[k] = pre[k - 1] + q[k];
+    for (int k = 1; k < DV; k++) pre[k] = __fadd_rn(pre[k - 1], q[k]);
     suf[DV - 1] = q[DV - 1];
 #pragma unroll
-    for (int k = DV - 2; k >= 0; k--) suf[k] = q[k] + suf[k + 1];
+    for (int k = DV - 2; k >= 0; k--) suf[k] = __fadd_rn(q[k], suf[k + 1]);
     if constexpr (DV == 1) {
         x[0] = 0.f;
     } else {
         x[0] = suf[1];
         x[DV - 1] = pre[DV - 2];
 #pragma unroll
-        for (int k = 1; k < DV - 1; k++) x[k] = pre[k - 1] + suf[k + 1];
+        for (int k = 1; k < DV - 1; k++) x[k] = __fadd_rn(pre[k - 1], suf[k + 1]);
     }
     return pre[DV - 1];
 }
@@ -172,20 +180,20 @@ __device__ __forceinline__ float var_node_spa(float (&x)[DV], int dv, float r)
 {
     float q[DV], pre[DV], suf[DV];     // pre[k] = q_0+..+q_k ; suf[k] = q_k+..+q_{DV-1}
 #pragma unroll
-    for (int k = 0; k < DV; k++) q[k] = (k < dv) ? x[k] + r : 0.f;
+    for (int k = 0; k < DV; k++) q[k] = (k < dv) ? __fadd_rn(x[k], r) : 0.f;
     pre[0] = q[0];
 #pragma unroll
-    for (int k = 1; k < DV; k++) pre[k] = pre[k - 1] + q[k];
+    for (int k = 1; k < DV; k++) pre[k] = __fadd_rn(pre[k - 1], q[k]);
     suf[DV - 1] = q[DV - 1];
 #pragma unroll
-    for (int k = DV - 2; k >= 0; k--) suf[k] = q[k] + suf[k + 1];
+    for (int k = DV - 2; k >= 0; k--) suf[k] = __fadd_rn(q[k], suf[k + 1]);
     if constexpr (DV == 1) {
         x[0] = 0.f;
     } else {
         x[0] = suf[1];
         x[DV - 1] = pre[DV - 2];
 #pragma unroll
-        for (int k = 1; k < DV - 1; k++) x[k] = pre[k - 1] + suf[k + 1];
+        for (int k = 1; k < DV - 1; k++) x[k] = __fadd_rn(pre[k - 1], suf[k + 1]);
     }
     return pre[DV - 1];
 }

@@ -45,11 +45,22 @@ int device_from_env()
     const char *s = std::getenv("LDPC535_DEVICE");
     return s ? std::atoi(s) : 0;
 }
-// How far the batcher speculates on a miss.
+// How far the batcher speculates on a miss.  A GPU call costs ~0.15-0.4 ms of latency whatever its
+// size while a window costs ~1 ns of kernel time, so the batcher buys as many windows per call as it
+// may need:
+//   tracking miss, link quiet      the next frames at the frame stride, current polarity
+//   search miss / link turbulent   a DENSE span: every offset from here on in both polarities.  A dense
+//                                  span answers every later request that falls inside it -- the search
+//                                  slides, the frames that follow a re-lock (offset - base is a multiple
+//                                  of 1), the -tx retries -- so a stream that keeps losing sync (Eb/N0
+//                                  0-2 dB: a loss every ~13 frames) costs one call per span instead of two
+//                                  per loss.  The span starts at 4096 offsets and doubles with every dense
+//                                  miss in a turbulent stretch (at most kSearchMax), so a clean
+//                                  acquisition stays cheap and a noisy buffer is covered in ~log2 calls.
 const long kTrackBatch = 1 << 16;   // frames at the frame stride
 const size_t kMaxEventLog = 65536;  // most recent sync events kept in d_events
-const long kSearchBatch = 2048;     // offsets, each in both polarities (a failed search costs one GPU call per 2048 slides;
-                                    // a GPU call is ~0.15 ms of latency whatever its size, 4096 windows are ~10 us of kernel)
+const long kSearchMin = 4096;       // offsets of the first dense span, each in both polarities
+const long kSearchMax = 1 << 18;    // 2 x 262 144 windows: ~0.6 ms of kernel, 2.6 MB of results
 }  // namespace
 
 ldpc_decoder_cb::sptr ldpc_decoder_cb::make(const int method)
@@ -62,7 +73,8 @@ ldpc_decoder_cb_impl::ldpc_decoder_cb_impl(const int method)
                 gr::io_signature::make(1, 1, sizeof(unsigned char))),
       d_method(method), d_M(0), d_N(0), d_nbytes(0), d_iterations(LDPC535_REF_ITERATIONS),
       d_early_stop(true), d_threshold(0), d_code(NULL), d_in(NULL), d_ninput(0), d_max_frames(0),
-      d_base(0), d_stride(1), d_count(0), d_pol_mask(0), d_batches(0), d_windows(0)
+      d_base(0), d_stride(1), d_count(0), d_pol_mask(0), d_span(kSearchMin), d_turbulent(0),
+      d_batches(0), d_windows(0)
 {
     const int st = ldpc535_code_create_default(device_from_env(), &d_code);
     if (st != LDPC535_OK)
@@ -99,7 +111,7 @@ void ldpc_decoder_cb_impl::fetch(long offset, int polarity, bool tracking)
     d_off.clear();
     d_pol.clear();
     d_base = offset;
-    if (tracking) {
+    if (tracking && d_turbulent == 0) {
         long n = (d_ninput - offset) / d_N;
         n = std::min(n, std::min(d_max_frames, kTrackBatch));
         n = std::max(n, 1L);
@@ -112,7 +124,8 @@ void ldpc_decoder_cb_impl::fetch(long offset, int polarity, bool tracking)
         }
     } else {
         long n = d_ninput - d_N - offset + 1;       // windows that still fit the input
-        n = std::max(1L, std::min(n, kSearchBatch));
+        n = std::max(1L, std::min(n, d_span));
+        d_span = std::min(kSearchMax, d_span * 2);  // the next dense miss of this stretch reaches twice as far
         d_stride = 1;
         d_count = n;
         d_pol_mask = 3;
@@ -166,11 +179,16 @@ int ldpc_decoder_cb_impl::general_work(int noutput_items, gr_vector_int &ninput_
     d_max_frames = noutput_items / d_nbytes;
     d_count = 0;                                    // results never outlive the input buffer
 
+    // a call that saw no sync loss ends a turbulent stretch: back to frame-stride batches and short spans
+    if (d_turbulent > 0) d_turbulent--;
+    if (d_turbulent == 0) d_span = kSearchMin;
+
     long consumed = 0;
     int produced = 0;
     try {
         produced = d_sync.run(*this, d_ninput, noutput_items, d_N, d_nbytes, d_threshold, out,
                               &consumed, [this](int ev) {
+                                  if (ev == EV_MAX_ERRORS) d_turbulent = 2;   // this call and the next one
                                   // bounded log for tests / monitoring: a flowgraph that never
                                   // reads it must not grow without limit
                                   if (d_events.size() >= kMaxEventLog)

@@ -35,6 +35,8 @@ private:
     long d_stride;           // N (tracking batch) or 1 (search batch)
     long d_count;            // windows per polarity in the cached batch
     int d_pol_mask;          // bit 0: +1 cached, bit 1: -1 cached
+    long d_span;             // offsets of the next dense span (doubles per dense miss in a turbulent stretch)
+    int d_turbulent;         // > 0: a sync loss happened in this general_work() or the one before
     std::vector<int64_t> d_off;
     std::vector<int8_t> d_pol;
     std::vector<uint8_t> d_bytes, d_synd;

@@ -33,6 +33,7 @@ SYMBOLS = {
     "ldpc535_code_get_generator": (_i, [_vp, _vp]),
     "ldpc535_code_kernel_name": (C.c_char_p, [_vp, _i]),
     "ldpc535_code_set_kernel": (_i, [_vp, C.c_char_p]),
+    "ldpc535_code_kernel_for": (C.c_char_p, [_vp, _i, _i, _sz]),
     "ldpc535_launch_count": (_u64, [_vp]),
     "ldpc535_pool_create": (_i, [_vp, _i, _i, _pi, _i, C.POINTER(_vp)]),
     "ldpc535_pool_destroy": (None, [_vp]),

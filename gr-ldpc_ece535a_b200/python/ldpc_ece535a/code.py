@@ -80,6 +80,9 @@ class Code:
     def kernel_name(self, method=_abi.METHOD_SUMPRODUCT):
         return lib().ldpc535_code_kernel_name(self._h, int(method)).decode()
 
+    def kernel_for(self, method, early_stop, n_win):
+        return lib().ldpc535_code_kernel_for(self._h, int(method), int(bool(early_stop)), int(n_win)).decode()
+
     def set_kernel(self, name):
         check(lib().ldpc535_code_set_kernel(self._h, None if name is None else name.encode()),
               "set_kernel")

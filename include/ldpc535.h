@@ -122,6 +122,10 @@ LDPC535_API int ldpc535_code_get_h(const ldpc535_code *code, int32_t *row_ptr, i
 LDPC535_API int ldpc535_code_get_generator(const ldpc535_code *code, uint32_t *P);
 /* Which decoder kernel family this code dispatches to: "c4-thread", "warp", "block". */
 LDPC535_API const char *ldpc535_code_kernel_name(const ldpc535_code *code, int method);
+/* The same for a particular call (early stop and the batch size take part in the dispatch): e.g. sum-product
+ * on the shipped code runs on "c4-thread" at fixed iterations and on "warp" with early stop. */
+LDPC535_API const char *ldpc535_code_kernel_for(const ldpc535_code *code, int method, int early_stop,
+                                                size_t n_win);
 
 /* ---- pinned host memory (optional; pageable pointers work, slower) -------- */
 LDPC535_API int ldpc535_host_alloc(size_t bytes, void **ptr);
@@ -192,8 +196,10 @@ LDPC535_API int ldpc535_decode_debug(ldpc535_code *code, const float *sym, size_
                                      float *out_L, float *out_E, float *out_M,
                                      uint8_t *out_bytes, uint8_t *out_iters);
 
-/* Force a kernel family for subsequent decode calls ("warp", "block", "c4-thread", "regular",
- * NULL/"auto" = default).  Returns LDPC535_ERR_UNSUPPORTED if the code cannot run on it.
+/* Force a kernel family for subsequent decode calls ("warp", "block", "c4-thread", "c4-refill", "regular",
+ * NULL/"auto" = default).  "c4-refill": thread-per-codeword kernel with per-codeword early stop and slot
+ * refill for the shipped code -- faster than "warp" on clean channels (Eb/N0 >= 6 dB), slower below; it
+ * applies to early-stop calls of >= 2 x 256 x SM-count windows and falls back to its siblings otherwise.  Returns LDPC535_ERR_UNSUPPORTED if the code cannot run on it.
  * Measurement knobs read from the environment at ldpc535_code_create* (results never change):
  * LDPC535_REGULAR_VARIANT=0 runs the (3,6)-regular n = 8192 code on the 1024-thread kernel instead
  * of the register-table one; LDPC535_ENCODER=generic keeps large codes on the AND/XOR scan encoder

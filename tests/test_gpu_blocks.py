@@ -150,3 +150,45 @@ def test_headless_txrx_writes_the_image(shipped, tmp_path):
         want, _ = blk.work(sym, payload.size)
         assert np.array_equal(r["decoded"], want), ebn0
         assert r["events"] == blk.events
+
+
+def test_headless_txrx_with_the_reference_image(shipped, tmp_path):
+    """BASELINE config 2 with the file it names: the reference's examples/mandril.bmp (committed as
+    tests/golden/mandril.bmp, 19 270 bytes) sent twice through encoder block -> AWGN -> decoder block
+    -> image_sink at Eb/N0 = noiseless, 0, 1, 2, 3, 4 dB.  Noiseless the sink writes the image back
+    byte for byte; at every Eb/N0 the decoded stream and the sync events equal the block-level
+    oracle's and -- where the prebuilt oracle/_ref travelled along -- the reference's own decoder
+    block's, driven over the same symbols."""
+    import importlib.util
+    import os
+    from oracle import ref as R
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("headless_txrx", os.path.join(root, "examples", "headless_txrx.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    image = np.fromfile(os.path.join(root, "tests", "golden", "mandril.bmp"), np.uint8)
+    assert image.size == 19270
+    payload = np.tile(image, 2)                      # 38 540 bytes = 9 635 whole frames
+    out = tmp_path / "result.bmp"
+    r = mod.run_chain(payload, None, 1, out_path=str(out), buf_frames=4096)
+    assert np.array_equal(r["decoded"], payload)
+    assert r["files"] == 1 and out.read_bytes() == image.tobytes()
+    assert r["events"] == [1]
+    sym0, _ = O.encoder_work(shipped["Hp"], shipped["L"], shipped["U"], payload, payload.size * 16)
+    for ebn0 in (0.0, 1.0, 2.0, 3.0, 4.0):
+        r = mod.run_chain(payload, ebn0, 1, out_path=str(out), buf_frames=4096, seed=int(ebn0) + 30)
+        rng = np.random.default_rng(int(ebn0) + 30)
+        sigma = np.float32(np.sqrt(10.0 ** (-ebn0 / 10.0)))
+        sym = sym0.copy()
+        sym.real += rng.standard_normal(sym.size, dtype=np.float32) * sigma
+        sym.imag += rng.standard_normal(sym.size, dtype=np.float32) * sigma
+        blk = O.DecoderBlock(shipped["Hp"], 1)
+        want, _ = blk.work(sym, payload.size)
+        assert np.array_equal(r["decoded"], want), ebn0
+        assert r["events"] == blk.events
+        if R.available() and ebn0 in (2.0, 4.0):      # the reference block decodes one window at a time on one core
+            ref = R.RefDecoder(1)
+            rout, _ = ref.work(sym, payload.size)
+            assert np.array_equal(r["decoded"], rout), ebn0
+            assert r["events"] == ref.events
+            ref.close()

@@ -849,3 +849,46 @@ def test_counter_based_synthetic_inputs(c4):
     # the C8k configuration uses 512-byte frames: 32 counter blocks per frame
     mufu = c4.probe_pipe_peak(L._abi.PIPE_MUFU)
     assert 2e12 < mufu < 6e12, mufu                                       # ~16 lanes/clk/SM x 148 SMs x ~1.9 GHz
+
+
+def test_c4_refill_kernel_matches_warp_kernel_and_oracle(c4, shipped):
+    """Early-stop sum-product on the shipped code with the opt-in persistent-slot kernel
+    (set_kernel("c4-refill"): decode_c4_refill_kernel -- per-codeword stop, slots refilled from an
+    atomic cursor, next window prefetched by cp.async), on batches large enough for it: bytes, syndrome weights and iteration counts equal the
+    warp-per-codeword kernel's on every frame at 2 / 6 / 10 dB for 5 and 50 iterations max, for ragged
+    batch sizes, with window offsets and polarities; a 30 000-frame slice equals the oracle."""
+    sms = L.device_info(0)["sm_count"]
+    big = sms * 256 * 2
+    n = big + 70_001
+    _, cw, _ = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], 4096, None, seed=91)
+    rng = np.random.default_rng(92)
+    clean = util.bpsk(cw)[rng.integers(0, 4096, n)]
+    for ebn0, iters in ((2.0, 5), (6.0, 5), (10.0, 5), (2.0, 50), (6.0, 3)):
+        sigma = np.float32(np.sqrt(10.0 ** (-ebn0 / 10.0)))
+        noisy = clean.copy()
+        noisy.real += rng.standard_normal(clean.shape, dtype=np.float32) * sigma
+        noisy.imag = rng.standard_normal(clean.shape, dtype=np.float32)          # ignored by the decoder
+        for cnt in (n, big, big + 1):
+            c4.set_kernel("warp")
+            want = c4.decode(noisy[:cnt], method=1, max_iters=iters, early_stop=True)
+            c4.set_kernel("c4-refill")
+            got = c4.decode(noisy[:cnt], method=1, max_iters=iters, early_stop=True)
+            for x, y, name in zip(got, want, ("bytes", "synd", "iters")):
+                assert np.array_equal(x, y), (ebn0, iters, cnt, name)
+        m = 30_000 if iters <= 5 else 2_000
+        assert c4.kernel_for(1, True, n) == "c4-refill" and c4.kernel_for(1, True, 1000) == "warp"
+        assert c4.kernel_for(1, False, n) == "c4-thread"
+        wb, wit, wsy = util.oracle_spa_batch(noisy[:m], shipped["Hp"], iters, True)
+        assert np.array_equal(got[0][:m], wb) and np.array_equal(got[2][:m], wit) and np.array_equal(got[1][:m], wsy)
+    # windows at arbitrary symbol offsets, both polarities
+    flat = noisy.reshape(-1)
+    offs = rng.integers(0, flat.size - 64, big + 333).astype(np.int64)
+    pol = rng.choice(np.array([-1, 1], np.int8), offs.size)
+    c4.set_kernel("warp")
+    want = c4.decode(flat, method=1, max_iters=5, early_stop=True, win_offset=offs, polarity=pol)
+    c4.set_kernel("c4-refill")
+    got = c4.decode(flat, method=1, max_iters=5, early_stop=True, win_offset=offs, polarity=pol)
+    c4.set_kernel(None)
+    assert c4.kernel_for(1, True, n) == "warp"          # the default dispatch for early stop
+    for x, y in zip(got, want):
+        assert np.array_equal(x, y)

@@ -205,6 +205,41 @@ def test_live_decisions_20k_frames(c4, method, ebn0):
 
 
 @live
+def test_live_ber_fer_sweep_matches_reference_simulator_convention(c4):
+    """The reference's stand-alone simulator (apps/ldpc_lapack.cpp:533-714) sweeps Eb/N0, sends random
+    frames through makeParityCheck -> 2u-1 -> + sqrt(N0) N(0,1) with N0 = 10^(-EbN0/10) (:626-642)
+    and counts bit and frame errors of its four decoders (:647-714).  Same experiment here, -2 ... 8 dB
+    in 1 dB steps, with the decoders of the reference build on one side and the CUDA decoders on the
+    other: info-bit error counts and frame error counts must be EQUAL for every method at every point
+    (they are sums over identical decisions), and the curve must behave (monotone FER for sum-product)."""
+    enc = R.RefEncoder()
+    n_of = {1: 1500, 0: 1500, 3: 1500, 2: 300}        # the reference's bit flipping is O(M N^2)
+    rng = np.random.default_rng(5350)
+    fer_spa = []
+    for ebn0 in range(-2, 9):
+        data = rng.integers(0, 256, 4 * 1500).astype(np.uint8)
+        sym, _ = enc.work(data, 64 * 1500)
+        sigma = np.float32(np.sqrt(10.0 ** (-ebn0 / 10.0)))
+        noisy = sym.copy()
+        noisy.real += rng.standard_normal(sym.size).astype(np.float32) * sigma
+        bits = np.unpackbits(data.reshape(-1, 4), axis=1)
+        for method in (1, 0, 2, 3):
+            n = n_of[method]
+            want, _, _ = R.decode_frames(noisy[:64 * n], method=method, iterations=5, threads=os.cpu_count() or 1)
+            got, _, _ = c4.decode(noisy[:64 * n], method=method, max_iters=5, early_stop=True)
+            eb_ref = int((np.unpackbits(want, axis=1) != bits[:n]).sum())
+            eb_gpu = int((np.unpackbits(got, axis=1) != bits[:n]).sum())
+            ef_ref = int((want != data.reshape(-1, 4)[:n]).any(axis=1).sum())
+            ef_gpu = int((got != data.reshape(-1, 4)[:n]).any(axis=1).sum())
+            assert (eb_gpu, ef_gpu) == (eb_ref, ef_ref), (ebn0, method)
+            assert np.array_equal(got, want), (ebn0, method)
+            if method == 1:
+                fer_spa.append(ef_gpu / n)
+    assert fer_spa[0] > 0.95 and fer_spa[-1] < 0.01
+    assert all(a >= b - 0.03 for a, b in zip(fer_spa, fer_spa[1:]))
+
+
+@live
 @pytest.mark.parametrize("method", [1, 0, 3])
 @pytest.mark.parametrize("ebn0", [None, 3.0, 5.0])
 def test_live_block_streams(method, ebn0):
