@@ -129,14 +129,22 @@ constexpr int kVarGroup = C4_VAR_GROUP;     // variables between barriers
 #define C4_GROUPS 1
 #endif
 constexpr int kGroups = C4_GROUPS;          // 1: all warps in lock step; 2, 3: rotated groups
-#ifndef C4_REG_R
-#define C4_REG_R 0
-#endif
 constexpr int kRegEdges = C4_REG_EDGES;
 constexpr int kSmemEdges = kE - kRegEdges;
-constexpr int kRegR = C4_REG_R;             // intrinsic values kept in registers; the rest in smem
-constexpr int kSmemR = kN - kRegR;          // (an r is read once per iteration, a message four times)
-constexpr size_t kSmemBytes = (size_t)kThreads * (kSmemEdges + kSmemR) * sizeof(float);
+// Intrinsic values: 64 shared-memory columns like the messages (same base register and constant
+// offsets in the iteration, so the compiler can order these loads freely against the message
+// stores), filled once per batch from a staging buffer of one 64-value row per thread into which
+// the NEXT batch's symbols are fetched asynchronously.  The row pitch of 65 words makes both
+// staging access patterns bank-conflict free: the fetch writes 32 consecutive words of one row,
+// the owner reads word i of 32 consecutive rows (banks row + i).
+constexpr int kRPitch = kN + 1;
+constexpr size_t kSmemBytes = (size_t)kThreads * (kSmemEdges + kN + kRPitch) * sizeof(float);
+
+__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 
 template <bool DEBUG>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -163,6 +171,36 @@ decode_c4_thread_kernel(const DecodeParams p)
         else asm volatile("bar.sync %0, %1;" :: "r"(1 + grp), "n"(NT / kGroups) : "memory");
     };
 
+    // Fetch of one batch's real parts into the staging rows, warp-cooperative and asynchronous: for
+    // codeword j of the warp's 32 every lane copies symbols `lane` and `lane + 32` with 4-byte
+    // cp.async, so one instruction reads 256 contiguous bytes of gr_complex (128 of packed reals)
+    // and writes 32 consecutive words of row j.  Issued one whole batch ahead: the load phase used
+    // to be 64 scalar loads per thread at a 512-byte stride between lanes with every warp of the SM
+    // waiting on them -- 10.5 us of a 36 us batch at 5 iterations (profiles/r2_iter_sweep.txt).
+    float *const rstage = c4_smem + (kSmemEdges + kN) * NT;
+    const int lane = threadIdx.x & 31;
+    const int elt = p.sym_re ? 1 : 2;               // floats per symbol
+    const float *const gsrc = (p.sym_re ? p.sym_re : reinterpret_cast<const float *>(p.sym)) + lane * elt;
+    auto fetch_batch = [&](long long base_b) {
+        const long long wb = base_b + threadIdx.x;
+        long long offb = -1;
+        if (wb < p.n_win) offb = p.win_offset ? p.win_offset[wb] : wb * (long long)kN;
+        const bool good = offb >= 0 && offb + kN <= p.n_sym;
+        const unsigned m = __ballot_sync(0xffffffffu, good);
+        float *dst = rstage + (threadIdx.x - lane) * kRPitch + lane;
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const long long oj = __shfl_sync(0xffffffffu, offb, j);
+            if ((m >> j) & 1u) {
+                const float *s = gsrc + oj * elt;
+                cp_async_4(dst + j * kRPitch, s);
+                cp_async_4(dst + j * kRPitch + 32, s + 32 * elt);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch_batch((long long)blockIdx.x * NT);
+
     // every thread of the CTA makes the same number of trips (barriers inside); threads past
     // the end of the batch compute on zeros and store nothing
     for (long long base = (long long)blockIdx.x * NT; base < p.n_win; base += stride) {
@@ -173,43 +211,22 @@ decode_c4_thread_kernel(const DecodeParams p)
         const bool ok = live && off >= 0 && off + kN <= p.n_sym;
 
         // ---- r_i = -pol * Re(sym_i)  (lib/ldpc_decoder_cb_impl.cc:149-153, :486) ----
+        // The real parts of this batch were fetched into the staging rows while the previous batch
+        // iterated (fetch_batch); scale them into the r columns, then start the next batch's fetch.
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
         float r[kN];
-        if (ok && p.sym_re) {
-            const float *s = p.sym_re + off;
-            if ((off & 3) == 0) {
-                const float4 *s4 = reinterpret_cast<const float4 *>(s);
+        {
+            const float *row = rstage + threadIdx.x * kRPitch;
 #pragma unroll
-                for (int i = 0; i < kN / 4; i++) {
-                    const float4 v = __ldg(s4 + i);
-                    r[4 * i] = __fmul_rn(npol, v.x); r[4 * i + 1] = __fmul_rn(npol, v.y);
-                    r[4 * i + 2] = __fmul_rn(npol, v.z); r[4 * i + 3] = __fmul_rn(npol, v.w);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < kN; i++) r[i] = __fmul_rn(npol, __ldg(s + i));
-            }
-        } else if (ok) {
-            const float2 *s = p.sym + off;
-            if ((off & 1) == 0) {
-                const float4 *s4 = reinterpret_cast<const float4 *>(s);
-#pragma unroll
-                for (int i = 0; i < kN / 2; i++) {
-                    const float4 v = __ldg(s4 + i);
-                    r[2 * i] = __fmul_rn(npol, v.x);
-                    r[2 * i + 1] = __fmul_rn(npol, v.z);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < kN; i++) r[i] = __fmul_rn(npol, __ldg(&s[i].x));
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < kN; i++) r[i] = 0.f;
+            for (int i = 0; i < kN; i++) r[i] = ok ? __fmul_rn(npol, row[i]) : 0.f;
         }
-        static_for<kSmemR>([&](auto ic) {
+        static_for<kN>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            ms[(kSmemEdges + i) * NT] = r[kRegR + i];
+            ms[(kSmemEdges + i) * NT] = r[i];
         });
+        __syncwarp();                      // every row of the warp has been read: the rows may be overwritten
+        if (base + stride < p.n_win) fetch_batch(base + stride);
         // M_ji = r_i on every edge (:489-496), stored as t = copysign(2^-|M|, M)
         static_for<kE>([&](auto ec) {
             constexpr int e = decltype(ec)::value;
@@ -266,9 +283,7 @@ decode_c4_thread_kernel(const DecodeParams p)
                         constexpr int e = kT.edge_of_col[a + k];
                         x[k] = msg_ld(std::integral_constant<int, e>{});
                     });
-                    float ri;
-                    if constexpr (i < kRegR) ri = r[i]; else ri = ms[(kSmemEdges + i - kRegR) * NT];
-                    L = var_node_spa<dv>(x, dv, ri);
+                    L = var_node_spa<dv>(x, dv, ms[(kSmemEdges + i) * NT]);
                     static_for<dv>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
                         constexpr int e = kT.edge_of_col[a + k];

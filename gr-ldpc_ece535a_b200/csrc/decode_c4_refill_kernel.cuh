@@ -36,12 +36,6 @@ constexpr int kRfRow = 33;
 constexpr int kRfWarpWords = 2 * kN * kRfRow;
 constexpr size_t kRfSmemBytes = ((size_t)kRfThreads * kSmemEdges + (size_t)(kRfThreads / 32) * kRfWarpWords) * sizeof(float);
 
-__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gmem_src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-
 __global__ void __launch_bounds__(kRfThreads, 1)
 decode_c4_refill_kernel(const DecodeParams p, unsigned int *__restrict__ cursor, const int refill_min)
 {

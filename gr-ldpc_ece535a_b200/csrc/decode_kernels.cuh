@@ -76,6 +76,12 @@ __device__ __forceinline__ T pad_msg()
 }
 
 // Re(symbol i) of either input layout
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 __device__ __forceinline__ float load_re(const DecodeParams &p, long long i)
 {
     return p.sym_re ? __ldg(p.sym_re + i) : __ldg(&p.sym[i].x);
@@ -154,18 +160,38 @@ decode_warp_kernel(const DecodeParams p)
     __syncwarp();
 
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    // The symbols of a window are fetched one window AHEAD with cp.async into a 64-word strip of the
+    // warp (no registers held across the iterations): a warp that loaded and then used them sat out
+    // the whole HBM latency once per codeword -- a fifth of all warp samples at 5 iterations (ncu,
+    // profiles/r2c_*).
+    float *stage = reinterpret_cast<float *>(smem_w + sizeof(T) * (blockDim.x >> 5) * ((DC + 2) * 32)) + warp * 64;
+    auto fetch_window = [&](long long wq) {
+        if (wq < p.n_win) {
+            const long long offq = p.win_offset ? p.win_offset[wq] : wq * (long long)N;
+            if (offq >= 0 && offq + N <= p.n_sym) {
+                const float *g = p.sym_re ? p.sym_re + offq : reinterpret_cast<const float *>(p.sym + offq);
+                const int elt = p.sym_re ? 1 : 2;
+                if (lane < N) cp_async_f32(stage + lane, g + lane * elt);
+                if (lane + 32 < N) cp_async_f32(stage + lane + 32, g + (lane + 32) * elt);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch_window((long long)blockIdx.x * (blockDim.x >> 5) + warp);
     for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w < p.n_win; w += warps_total) {
         const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
         const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
         const bool ok = off >= 0 && off + N <= p.n_sym;
         constexpr float kIn = (METHOD == kMethodSpa) ? kSpaScale : 1.f;      // SPA works in units of ln 2
         constexpr float kOut = (METHOD == kMethodSpa) ? kSpaUnscale : 1.f;   // (message dumps only)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");    // each lane reads back its own two words
         T r[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
             const int v = lane + 32 * t;
-            r[t] = (T)((ok && v < N) ? __fmul_rn(-pol * kIn, load_re(p, off + v)) : 0.f);
+            r[t] = (T)((ok && v < N) ? __fmul_rn(-pol * kIn, stage[v]) : 0.f);
         }
+        fetch_window(w + warps_total);
         float rk[2][DV];                               // r on a real edge of the bit, 0 on an unused slot
 #pragma unroll
         for (int t = 0; t < 2; t++)

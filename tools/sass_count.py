@@ -2,7 +2,7 @@
 """Instruction mix of the loops of one kernel in libldpc535.so (cuobjdump -sass), to state
 per-iteration instruction counts in DESIGN.md / bench.py without running anything.
 
-    python tools/sass_count.py 'decode_warp_kernelILi0ELi6ELi3ELb0'      # min-sum warp kernel
+    python tools/sass_count.py 'decode_warp_kernelILi0ELi6ELi3ELb0' [binary]     # min-sum warp kernel
 
 Prints every backward branch (= loop) with its address range, instruction count and opcode
 histogram; fp64-pipe instructions (D*) are summed separately.
@@ -19,7 +19,8 @@ SO = os.path.join(ROOT, "gr-ldpc_ece535a_b200", "libldpc535.so")
 
 def main():
     pat = re.compile(sys.argv[1])
-    sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
+    so = sys.argv[2] if len(sys.argv) > 2 else SO           # optional: another binary (a microbenchmark)
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
     on, ins = False, []
     for line in sass.splitlines():
         if "Function :" in line:
