@@ -152,6 +152,7 @@ decode_c4_thread_kernel(const DecodeParams p)
 {
     extern __shared__ float c4_smem[];
     constexpr int NT = kThreads;
+    if (p.select && *p.select != p.select_want) return;      // the other family was picked for these windows
     float *ms = c4_smem + threadIdx.x;
     float mreg[kRegEdges];
     auto msg_ld = [&](auto ec) -> float {

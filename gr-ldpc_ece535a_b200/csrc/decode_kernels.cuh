@@ -44,7 +44,40 @@ struct DecodeParams {
     int tabA_bytes, tabB_bytes;   // padded to 16 B
     // register-table regular kernel: windows are handed out by an atomic cursor (starts at 0)
     unsigned int *cursor;
+    // "c4-adaptive": two kernel families are queued for the same windows and a device-side word
+    // written by pick_family_kernel says which one runs; the other returns at once
+    const int *select;            // or nullptr: run
+    int select_want;
 };
+
+// Device-side choice between the lock-step thread-per-codeword kernel and the warp-per-codeword
+// kernel for an early-stop batch (both give identical outputs; only the time differs).  A lock-step
+// CTA runs until the slowest of its 256 codewords stops, a warp until its own codeword stops.  From
+// the iteration counts of a decoded sample: q_k = share of codewords that ran >= k iterations;
+//   lock step:  t0 + t1 * sum_k (1 - (1 - q_k)^256)      warp:  u0 + u1 * sum_k q_k
+// with the per-batch constants measured on B200 (us per 256 codewords per SM, profiles/r2_iter_sweep.txt).
+__global__ void __launch_bounds__(256) pick_family_kernel(const uint8_t *iters, int n, int max_iters, int *select)
+{
+    __shared__ int hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) atomicAdd(&hist[iters[i]], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int valid = 0;
+        for (int k = 1; k <= max_iters && k < 255; k++) valid += hist[k];      // 255 marks a refused window
+        float lock = 0.f, mean = 0.f;
+        int ge = valid;                                                        // codewords with iters >= k
+        for (int k = 1; k <= max_iters && k < 255; k++) {
+            const float q = valid ? (float)ge / (float)valid : 1.f;
+            mean += q;
+            lock += 1.f - __powf(1.f - q, 256.f);
+            ge -= hist[k];
+        }
+        const float t_lock = 4.5f + 5.3f * lock, t_warp = 8.7f + 5.95f * mean;
+        *select = (t_lock < t_warp) ? 1 : 0;
+    }
+}
 
 constexpr int kWarpKernelThreads = 128;
 #ifndef WARP_MIN_BLOCKS
@@ -107,6 +140,7 @@ decode_warp_kernel(const DecodeParams p)
 {
     using T = msg_t<METHOD>;
     extern __shared__ __align__(16) unsigned char smem_w[];
+    if (p.select && *p.select != p.select_want) return;      // the other family was picked for these windows
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // strip of this warp: DC rows of 32 messages (layout: code_tables.cpp color_warp_layout), one row

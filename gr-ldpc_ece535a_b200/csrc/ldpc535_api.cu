@@ -46,7 +46,8 @@ int fail(int status, const std::string &msg)
             return fail(LDPC535_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4, kHard64 = 5, kC4Refill = 6 };
+constexpr long long kAdaptiveSample = 16384;     // windows decoded first to pick the family ("c4-adaptive")
+enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 4, kHard64 = 5, kC4Refill = 6, kC4Adaptive = 7 };
 
 constexpr int kSlots = 3;                       // pipeline depth of the host-buffer API
 constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot (upper bound; slots grow on demand)
@@ -83,6 +84,8 @@ struct ldpc535_code {
     unsigned int *d_cursor = nullptr; // window cursors of the register-table kernel (one per launch in flight, round-robin)
     unsigned int cursor_launch = 0;
     int c4_refill_min = 1;            // "c4-refill": lanes of a warp that must be waiting before its slots are refilled
+    int *d_select = nullptr;          // "c4-adaptive": family words (one per launch in flight, round-robin) + sample iteration counts
+    unsigned int select_launch = 0;
     bool fits_regular = false;
     int regular_variant = 1;          // 1: 512-thread register-table kernel (fixed sizes), 0: 1024-thread kernel
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
@@ -258,7 +261,7 @@ void release(ldpc535_code *c)
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
-    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_cursor); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_cursor); cudaFree(c->d_select); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
     delete c;
 }
 
@@ -269,6 +272,7 @@ int family_from_name(const char *name, int *out)
     if (!strcmp(name, "block")) { *out = kBlock; return 0; }
     if (!strcmp(name, "c4-thread")) { *out = kC4Thread; return 0; }
     if (!strcmp(name, "c4-refill")) { *out = kC4Refill; return 0; }
+    if (!strcmp(name, "c4-adaptive")) { *out = kC4Adaptive; return 0; }
     if (!strcmp(name, "regular")) { *out = kRegular; return 0; }
     return 1;
 }
@@ -292,11 +296,20 @@ int resolve_family(const ldpc535_code *c, int forced, int method, int early_stop
         // at 5 iterations max it is 1.02x / 0.89x / 1.00x / 1.23x as fast at Eb/N0 = 2 / 4 / 6 / 8 dB and
         // 0.77x at 50 iterations max, 2 dB (profiles/r2_refill_sweep.txt) -- a win only on clean channels.
         else if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && !early_stop) f = kC4Thread;
+        // Early stop on a batch that fills the GPU several times over: a sample is decoded first and
+        // the device picks lock-step thread-per-codeword (frames that mostly run to max_iters: +17 % at
+        // 2 dB, 5 iterations) or warp-per-codeword (frames that stop early) for the rest.
+        else if (c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT && early_stop) f = kC4Adaptive;
         else if (c->fits_regular && method == LDPC535_METHOD_SUMPRODUCT) f = kRegular;
         else if (c->fits_warp) f = kWarp;
         else f = kBlock;
     }
     if (f == kC4Thread && !(c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
+    if (f == kC4Adaptive) {
+        if (!(c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
+        if (!early_stop) f = kC4Thread;
+        else if (n_win < (long long)c->sm_count * c4::kThreads * 4 + kAdaptiveSample) f = kWarp;
+    }
     if (f == kC4Refill) {
         if (!(c->is_c4 && method == LDPC535_METHOD_SUMPRODUCT)) return -1;
         // early stop and batches that fill the GPU twice over (and fit its 32-bit offsets); else its siblings
@@ -427,6 +440,39 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
                 e = cudaGetLastError();
             }
         }
+    } else if (family == kC4Adaptive && !dbg) {
+        // 1. the first kAdaptiveSample windows on the warp kernel; 2. pick_family_kernel turns their
+        // iteration counts into the family word; 3. + 4. both families are queued for the remaining
+        // windows and the one not picked returns at once.  Everything stays on the stream.
+        if (!c->d_select && cudaMalloc(reinterpret_cast<void **>(&c->d_select), 64 * (sizeof(int) + kAdaptiveSample)) != cudaSuccess)
+            return fail(LDPC535_ERR_CUDA, "family word allocation");
+        const unsigned slot = c->select_launch++ & 63u;
+        int *select = c->d_select + slot;
+        uint8_t *sample_iters = reinterpret_cast<uint8_t *>(c->d_select + 64) + (size_t)slot * kAdaptiveSample;
+        DecodeParams head = p;
+        head.n_win = kAdaptiveSample;
+        if (!head.out_iters) head.out_iters = sample_iters;
+        e = launch_generic<6, 3>(c, kWarp, method, false, head, st);
+        if (e == cudaSuccess) {
+            pick_family_kernel<<<1, 256, 0, st>>>(head.out_iters, (int)kAdaptiveSample, p.max_iters, select);
+            e = cudaGetLastError();
+        }
+        DecodeParams rest = p;
+        const long long S = kAdaptiveSample;
+        rest.n_win = p.n_win - S;
+        if (p.win_offset) rest.win_offset = p.win_offset + S;
+        else {                                            // aligned frames: shift the symbol base instead
+            if (p.sym_re) rest.sym_re = p.sym_re + S * p.N; else rest.sym = p.sym + S * p.N;
+            rest.n_sym = p.n_sym - S * p.N;
+        }
+        if (p.polarity) rest.polarity = p.polarity + S;
+        rest.out_bytes = p.out_bytes + S * p.nbytes;
+        if (p.out_synd) rest.out_synd = p.out_synd + S;
+        if (p.out_iters) rest.out_iters = p.out_iters + S;
+        rest.select = select;
+        if (e == cudaSuccess) { rest.select_want = 1; e = launch_c4_thread(rest, false, c->sm_count, st); }
+        if (e == cudaSuccess) { rest.select_want = 0; e = launch_generic<6, 3>(c, kWarp, method, false, rest, st); }
+        if (e == cudaSuccess) c->launches += 3;
     } else if (family == kC4Refill && !dbg && p.n_sym < (1ll << 32)) {
         if (!c->d_cursor && cudaMalloc(reinterpret_cast<void **>(&c->d_cursor), 64 * sizeof(unsigned int)) != cudaSuccess)
             return fail(LDPC535_ERR_CUDA, "cursor allocation");
@@ -434,7 +480,7 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
         if ((e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st)) != cudaSuccess)
             return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
         e = launch_c4_refill(p, cursor, c->c4_refill_min, c->sm_count, st);
-    } else if (family == kC4Thread || family == kC4Refill) e = launch_c4_thread(p, dbg, c->sm_count, st);
+    } else if (family == kC4Thread || family == kC4Refill || family == kC4Adaptive) e = launch_c4_thread(p, dbg, c->sm_count, st);
     else if (c->dc_t == 6) e = launch_generic<6, 3>(c, family, method, dbg, p, st);
     else e = launch_generic<16, 8>(c, family, method, dbg, p, st);
     if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("decode launch: ") + cudaGetErrorString(e));
@@ -730,6 +776,7 @@ const char *ldpc535_code_kernel_name(const ldpc535_code *c, int method)
     case kBlock: return "block";
     case kC4Thread: return "c4-thread";
     case kC4Refill: return "c4-refill";
+    case kC4Adaptive: return "c4-adaptive";
     case kRegular: return "regular";
     case kHard64: return "hard64";
     default: return "unsupported";
@@ -743,6 +790,7 @@ const char *ldpc535_code_kernel_for(const ldpc535_code *c, int method, int early
     const int f = resolve_family(c, c->forced, m, early_stop ? 1 : 0, (long long)n_win);
     switch (f) {
     case kC4Refill: return "c4-refill";
+    case kC4Adaptive: return "c4-adaptive";
     case kWarp: return "warp";
     case kBlock: return "block";
     case kC4Thread: return "c4-thread";
@@ -759,7 +807,7 @@ int ldpc535_code_set_kernel(ldpc535_code *c, const char *kernel)
     if (family_from_name(kernel, &f)) return fail(LDPC535_ERR_INVALID, "unknown kernel family");
     if (f == kWarp && !c->fits_warp) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the warp kernel");
     if (f == kBlock && !c->fits_block) return fail(LDPC535_ERR_UNSUPPORTED, "code does not fit the block kernel");
-    if ((f == kC4Thread || f == kC4Refill) && !c->is_c4) return fail(LDPC535_ERR_UNSUPPORTED, "not the shipped 32x64 code");
+    if ((f == kC4Thread || f == kC4Refill || f == kC4Adaptive) && !c->is_c4) return fail(LDPC535_ERR_UNSUPPORTED, "not the shipped 32x64 code");
     if (f == kRegular && !c->fits_regular) return fail(LDPC535_ERR_UNSUPPORTED, "not a (3,6)-regular code that fits shared memory");
     c->forced = f;
     return LDPC535_OK;

@@ -892,3 +892,39 @@ def test_c4_refill_kernel_matches_warp_kernel_and_oracle(c4, shipped):
     assert c4.kernel_for(1, True, n) == "warp"          # the default dispatch for early stop
     for x, y in zip(got, want):
         assert np.array_equal(x, y)
+
+
+def test_c4_adaptive_family_equals_warp_kernel(c4, shipped):
+    """Early stop on a batch that fills the GPU several times over ("c4-adaptive", the default there):
+    a 16 384-window sample goes through the warp kernel, pick_family_kernel chooses on the device,
+    and the rest runs on the lock-step thread kernel (noisy channel) or the warp kernel (clean
+    channel).  Bytes, syndrome weights and iteration counts equal the warp kernel's on every frame
+    whichever family was picked, for ragged sizes, with window offsets and polarities."""
+    sms = L.device_info(0)["sm_count"]
+    n = sms * 256 * 4 + 16384 + 4099
+    assert c4.kernel_for(1, True, n) == "c4-adaptive" and c4.kernel_for(1, True, n - 4100) == "warp"
+    assert c4.kernel_for(1, False, n) == "c4-thread"
+    _, cw, _ = util.synth_frames(shipped["Hp"], shipped["L"], shipped["U"], 4096, None, seed=93)
+    rng = np.random.default_rng(94)
+    clean = util.bpsk(cw)[rng.integers(0, 4096, n)]
+    for ebn0, iters in ((1.0, 5), (9.0, 5), (4.0, 7), (2.0, 20)):
+        sigma = np.float32(np.sqrt(10.0 ** (-ebn0 / 10.0)))
+        noisy = clean.copy()
+        noisy.real += rng.standard_normal(clean.shape, dtype=np.float32) * sigma
+        c4.set_kernel("warp")
+        want = c4.decode(noisy, method=1, max_iters=iters, early_stop=True)
+        c4.set_kernel(None)
+        before = c4.launch_count()
+        got = c4.decode(noisy, method=1, max_iters=iters, early_stop=True)
+        assert c4.launch_count() == before + 4          # sample, pick, and both families queued for the rest
+        for x, y, name in zip(got, want, ("bytes", "synd", "iters")):
+            assert np.array_equal(x, y), (ebn0, iters, name)
+    flat = noisy.reshape(-1)
+    offs = rng.integers(0, flat.size - 64, n).astype(np.int64)
+    pol = rng.choice(np.array([-1, 1], np.int8), offs.size)
+    c4.set_kernel("warp")
+    want = c4.decode(flat, method=1, max_iters=5, early_stop=True, win_offset=offs[:-1], polarity=pol[:-1])
+    c4.set_kernel(None)
+    got = c4.decode(flat, method=1, max_iters=5, early_stop=True, win_offset=offs[:-1], polarity=pol[:-1])
+    for x, y in zip(got, want):
+        assert np.array_equal(x, y)

@@ -14,18 +14,18 @@ gen = torch.Generator(device="cuda"); gen.manual_seed(1)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 codes = {}
 base = L.Code(None, device=0)
-for name, env in [("warp", None), ("lockstep", None)] + \
-                 [("refill%d" % r, {"LDPC535_C4_REFILL_MIN": str(r)}) for r in (1, 4, 8, 12, 16, 24, 32)]:
+for name, env in [("warp", None), ("lockstep", None), ("adaptive", None)] + \
+                 [("refill%d" % r, {"LDPC535_C4_REFILL_MIN": str(r)}) for r in (1, 8, 16)]:
     for k, v in (env or {}).items():
         os.environ[k] = v
     c = L.Code(None, device=0)
     for k in (env or {}):
         del os.environ[k]
-    c.set_kernel("warp" if name == "warp" else "c4-thread" if name == "lockstep" else "c4-refill")
+    c.set_kernel("warp" if name == "warp" else "c4-thread" if name == "lockstep" else "c4-adaptive" if name == "adaptive" else "c4-refill")
     codes[name] = c
 ob = torch.empty((n, 4), dtype=torch.uint8, device="cuda"); os_ = torch.empty(n, dtype=torch.uint8, device="cuda"); oi = torch.empty(n, dtype=torch.uint8, device="cuda")
 ref = None
-for ebn0, iters in ((2.0, 5), (4.0, 5), (6.0, 5), (8.0, 5), (2.0, 50), (6.0, 50)):
+for ebn0, iters in ((0.0, 5), (2.0, 5), (3.0, 5), (4.0, 5), (6.0, 5), (8.0, 5), (2.0, 10), (2.0, 50), (6.0, 50)):
     data, sym = synth(base, n, ebn0, sp, gen)
     row, ref = [], None
     for name, c in codes.items():
