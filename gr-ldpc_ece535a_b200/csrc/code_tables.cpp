@@ -150,6 +150,95 @@ void place_checks_for_banks(CodeTables &t)
     t.bank_groups = n_groups;
 }
 
+// Proper edge colouring of a bipartite multigraph with 32 colours (every node of degree <= 32:
+// Koenig), alternating-path algorithm.  eu / ev: left / right node of every edge.
+void edge_color_32(const std::vector<int> &eu, const std::vector<int> &ev, int n_left, int n_right,
+                   std::vector<int> &color)
+{
+    const int E = (int)eu.size();
+    color.assign(E, -1);
+    std::vector<int> at_u((size_t)n_left * 32, -1), at_v((size_t)n_right * 32, -1);   // node, colour -> edge
+    std::vector<int> path;
+    for (int e = 0; e < E; e++) {
+        const int u = eu[e], v = ev[e];
+        int a = 0, b = 0;
+        while (at_u[(size_t)u * 32 + a] >= 0) a++;          // free at u
+        while (at_v[(size_t)v * 32 + b] >= 0) b++;          // free at v
+        if (a != b) {
+            // walk the a/b alternating path from v (it cannot reach u) and swap its colours
+            path.clear();
+            int node = v, col = a;
+            bool on_right = true;
+            while (true) {
+                const int f = on_right ? at_v[(size_t)node * 32 + col] : at_u[(size_t)node * 32 + col];
+                if (f < 0) break;
+                path.push_back(f);
+                node = on_right ? eu[f] : ev[f];
+                on_right = !on_right;
+                col = (col == a) ? b : a;
+            }
+            for (int f : path) { at_u[(size_t)eu[f] * 32 + color[f]] = -1; at_v[(size_t)ev[f] * 32 + color[f]] = -1; }
+            for (int f : path) {
+                color[f] = (color[f] == a) ? b : a;
+                at_u[(size_t)eu[f] * 32 + color[f]] = f;
+                at_v[(size_t)ev[f] * 32 + color[f]] = f;
+            }
+        }
+        color[e] = a;
+        at_u[(size_t)u * 32 + a] = e;
+        at_v[(size_t)v * 32 + a] = e;
+    }
+}
+
+// Conflict-free layout for the register-table kernel (see code_tables.h: row_color).  A check's
+// messages stay in its storage column's ROW (32 consecutive columns), slot-major as before, but
+// inside the row each (column, slot) word sits at the bank its edge was coloured with: the check
+// phase reads a permutation of one row (conflict-free whatever the permutation), the variable
+// phase reads, per warp and k, 32 edges that all differ in colour.  Padded slots of a row take
+// the colours left over.
+void color_regular_rows(CodeTables &t)
+{
+    const int M = t.M, N = t.N, DC = t.dc_max, DV = t.dv_max, E = t.E;
+    std::vector<int> eu(E), ev(E), color;
+    for (int j = 0; j < M; j++)
+        for (int e = t.row_ptr[j], s = 0; e < t.row_ptr[j + 1]; e++, s++) eu[e] = (t.chk_pos[j] / 32) * DC + s;
+    for (int c = 0; c < N; c++)
+        for (int q = t.col_ptr[c], k = 0; q < t.col_ptr[c + 1]; q++, k++)
+            ev[t.edge_of_col[q]] = (c / 32) * DV + k;
+    edge_color_32(eu, ev, (M / 32) * DC, ((N + 31) / 32) * DV, color);
+    t.row_color.assign((size_t)M * DC, 0xFF);
+    for (int j = 0; j < M; j++)
+        for (int e = t.row_ptr[j], s = 0; e < t.row_ptr[j + 1]; e++, s++)
+            t.row_color[(size_t)t.chk_pos[j] * DC + s] = (uint8_t)color[e];
+    for (int row = 0; row < M / 32; row++)
+        for (int s = 0; s < DC; s++) {
+            bool used[32] = {};
+            for (int l = 0; l < 32; l++) {
+                const uint8_t c = t.row_color[(size_t)(row * 32 + l) * DC + s];
+                if (c != 0xFF) used[c] = true;
+            }
+            int nb = 0;
+            for (int l = 0; l < 32; l++) {
+                uint8_t &c = t.row_color[(size_t)(row * 32 + l) * DC + s];
+                if (c != 0xFF) continue;
+                while (used[nb]) nb++;
+                c = (uint8_t)nb;
+                used[nb] = true;
+            }
+        }
+    t.var_slot_colored.assign((size_t)DV * N, 0xFFFF);
+    for (int j = 0; j < M; j++)
+        for (int e = t.row_ptr[j], s = 0; e < t.row_ptr[j + 1]; e++, s++) {
+            const int col = t.chk_pos[j];
+            // position of this edge among its bit's edges (rows ascending)
+            const int c = t.col_idx[e];
+            int k = 0;
+            for (int q = t.col_ptr[c]; q < t.col_ptr[c + 1]; q++, k++)
+                if (t.edge_of_col[q] == e) break;
+            t.var_slot_colored[(size_t)k * N + c] = (uint16_t)(s * M + (col & ~31) + color[e]);
+        }
+}
+
 // Shared-memory layout of the warp-per-codeword kernel.  The strip of a codeword is dc_max rows
 // of 32 words; the message of (check j, slot s) lives in row s at a bank chosen per EDGE.  Lane j
 // reads row s in the check phase; in the variable phase lane l reads the k-th edge of bit
@@ -380,6 +469,7 @@ int build_code_tables(const int32_t *row_ptr_in, const int32_t *col_idx_in, int 
                 t.var_slot[(size_t)k * N + c] = (uint16_t)t.edge_slot[t.edge_of_col[q]];
     }
     if (M <= 32 && N <= 64) color_warp_layout(t);
+    if (M >= 64 && M % 32 == 0 && (size_t)t.dc_max * M <= 65535) color_regular_rows(t);
     return 0;
 }
 

@@ -37,6 +37,11 @@ struct CodeTables {
     std::vector<uint8_t> chk_deg_slot;  // [M]  degree of the check stored in column c
     int bank_extra_wavefronts = 0;      // variable-phase access groups' wavefronts beyond one
     int bank_groups = 0;
+    // Register-table kernel for (3,6)-regular codes: on top of the storage columns, the 32 words of a
+    // row (32 consecutive columns of one slot) are permuted by a proper 32-edge-colouring of the
+    // bipartite multigraph {(row, slot)} x {(bit warp, k)}: BOTH phases are bank-conflict free.
+    std::vector<uint8_t> row_color;     // [M][dc_max]  bank of (storage column, slot) inside its row; empty if not built
+    std::vector<uint16_t> var_slot_colored;   // [dv_max][N]  message index under that layout
     // warp-per-codeword kernel (M <= 32, N <= 64): conflict-free shared-memory strip layout
     std::vector<uint16_t> w_chk_pos;    // [dc_max][32]  position of (slot s, check lane), padded slots included
     std::vector<uint16_t> w_var_pos;    // [dv_max][64]  position of the k-th edge of a bit, or 0xFFFF

@@ -193,30 +193,59 @@ decode_regular_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row
 // iterations.  What was tried on top and rejected is in profiles/r1_microbench.txt (two codewords
 // per CTA half an iteration apart, explicit load/compute/store batching, 256 and 1024 threads,
 // r or the table back in shared memory).
-// Shared memory: msg[DC*M] | hard[N/32] | red.
+// Shared memory: msg[DC*M] | r[N] | hard[N/32] | red.
 template <int DC, int MF, int NF>
 __host__ __device__ constexpr size_t regular_rt_smem_bytes()
 {
-    return 4 * (size_t)DC * MF + 4 * (size_t)(NF / 32) + 16;
+    return 4 * (size_t)DC * MF + 4 * (size_t)NF + 4 * (size_t)(NF / 32) + 16;
 }
 
 template <int DC, int DV, int MF, int NF>
 __global__ void __launch_bounds__(512, 1)
-decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row4)
+decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_row4, const uint32_t *__restrict__ chk_color)
 {
     static_assert(DV == 3, "three message addresses per bit");
     static_assert(MF % 512 == 0 && NF % 512 == 0, "fixed sizes are whole multiples of the CTA");
     constexpr int NT = 512, CQ = MF / NT, BQ = NF / NT, M = MF, N = NF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *msg = reinterpret_cast<float *>(smem_raw);
-    uint32_t *hard = reinterpret_cast<uint32_t *>(msg + (size_t)DC * M);
+    float *rsm = msg + (size_t)DC * M;                     // intrinsic values, word q * NT + tid = bit of this thread
+    uint32_t *hard = reinterpret_cast<uint32_t *>(rsm + N);
     int *red = reinterpret_cast<int *>(hard + N / 32);
     const int tid = threadIdx.x, lane = tid & 31;
 
     // the address rows of this thread's bits: once per CTA, coalesced 8-byte loads
-    uint2 vt[BQ];
+    // three 16-bit message addresses per bit, packed: vx[q] = a0 | a1 << 16, vy[q / 2] = a2 of bits q, q + 1
+    uint32_t vx[BQ], vy[BQ / 2];
 #pragma unroll
-    for (int q = 0; q < BQ; q++) vt[q] = __ldg(reinterpret_cast<const uint2 *>(var_row4) + q * NT + tid);
+    for (int q = 0; q < BQ; q += 2) {
+        const uint2 ta = __ldg(reinterpret_cast<const uint2 *>(var_row4) + q * NT + tid);
+        const uint2 tb = __ldg(reinterpret_cast<const uint2 *>(var_row4) + (q + 1) * NT + tid);
+        vx[q] = ta.x; vx[q + 1] = tb.x;
+        vy[q / 2] = (ta.y & 0xffffu) | (tb.y << 16);
+    }
+    auto a0 = [&](int q) { return vx[q] & 0xffffu; };
+    auto a1 = [&](int q) { return vx[q] >> 16; };
+    auto a2 = [&](int q) { return (q & 1) ? (vy[q / 2] >> 16) : (vy[q / 2] & 0xffffu); };
+    // Coloured rows (code_tables.cpp: color_regular_rows): the word of (column j, slot s) sits in j's
+    // row of 32 columns at the bank its edge was coloured with, so the check phase reads a permutation
+    // of a row and the variable phase 32 different banks -- no bank conflict in either phase (the
+    // variable phase ran at 2.0 wavefronts per access with whole columns placed by bank).  The byte
+    // offsets of this thread's 8 x 6 check words (row start + 4 x colour; the slot's s * M * 4 is an
+    // immediate) are kept two per register; the intrinsic values moved to shared memory to make room.
+    uint32_t ck[CQ][DC / 2];
+#pragma unroll
+    for (int q = 0; q < CQ; q++) {
+        const uint32_t cw = __ldg(chk_color + q * NT + tid);         // slot s at bits 5s+2 .. 5s+6
+        const uint32_t rowb = (uint32_t)(q * NT + (tid - lane)) * 4u;
+#pragma unroll
+        for (int s = 0; s < DC; s += 2)
+            ck[q][s / 2] = (rowb + ((cw >> (5 * s)) & 0x7cu)) | ((rowb + ((cw >> (5 * s + 5)) & 0x7cu)) << 16);
+    }
+    auto chk_word = [&](int q, int s) -> float * {
+        const uint32_t off = (s & 1) ? (ck[q][s / 2] >> 16) : (ck[q][s / 2] & 0xffffu);
+        return reinterpret_cast<float *>(reinterpret_cast<char *>(msg + s * M) + off);
+    };
 
     const bool tag = p.early_stop != 0;
     const uint32_t tagmask = tag ? 0x40000000u : 0u;
@@ -233,6 +262,8 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
         float r[BQ];
 #pragma unroll
         for (int q = 0; q < BQ; q++) r[q] = ok ? __fmul_rn(-pol * kSpaScale, load_re(p, off + q * NT + tid)) : 0.f;
+#pragma unroll
+        for (int q = 0; q < BQ; q++) rsm[q * NT + tid] = r[q];        // read back by this thread only
         __syncthreads();                                   // previous window fully drained; red[1] visible
         const long long w_next = (long long)(unsigned int)red[1];
         // pull the next window of this CTA towards L2 while this one iterates (one 128-byte line per thread)
@@ -250,9 +281,9 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
 #pragma unroll
         for (int q = 0; q < BQ; q++) {
             const float t = to_check_msg(r[q]);
-            msg[vt[q].x & 0xffffu] = t;
-            msg[vt[q].x >> 16] = t;
-            msg[vt[q].y & 0xffffu] = t;
+            msg[a0(q)] = t;
+            msg[a1(q)] = t;
+            msg[a2(q)] = t;
         }
         __syncthreads();
 
@@ -263,13 +294,13 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
             uint32_t tagbad = 0;
 #pragma unroll
             for (int q = 0; q < CQ; q++) {
-                const int j = q * NT + tid;
                 float m[DC];
+                float *wd[DC];
 #pragma unroll
-                for (int s = 0; s < DC; s++) m[s] = msg[s * M + j];
+                for (int s = 0; s < DC; s++) { wd[s] = chk_word(q, s); m[s] = *wd[s]; }
                 tagbad |= check_node_spa<DC, true>(m);
 #pragma unroll
-                for (int s = 0; s < DC; s++) msg[s * M + j] = m[s];
+                for (int s = 0; s < DC; s++) *wd[s] = m[s];
             }
             if (tag) {
                 const int bad = __syncthreads_or((int)(tagbad & 0x40000000u));
@@ -278,11 +309,23 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
                 __syncthreads();
             }
             // ---- variable nodes: L, hard decision, next messages (tagged with the decision) ----
+            // Software-pipelined by hand: the messages of bit q + 1 are loaded BEFORE those of bit q are
+            // stored.  The compiler cannot do it -- to it the stores may alias the next loads -- and
+            // without it every bit paid the full shared-memory latency between its predecessor's stores
+            // and its own loads (ncu source view, profiles/r2b: the first FADD after each load group held
+            // 53 % of the variable phase's samples).  Distinct bits never share a message word.
+            float xn[DV] = {msg[a0(0)], msg[a1(0)], msg[a2(0)]};
+            float rn = rsm[tid];
 #pragma unroll
             for (int q = 0; q < BQ; q++) {
-                const int i0 = (int)(vt[q].x & 0xffffu), i1 = (int)(vt[q].x >> 16), i2 = (int)(vt[q].y & 0xffffu);
-                float x[DV] = {msg[i0], msg[i1], msg[i2]};
-                const float L = var_node_spa<DV>(x, DV, r[q]);
+                const int i0 = (int)a0(q), i1 = (int)a1(q), i2 = (int)a2(q);
+                float x[DV] = {xn[0], xn[1], xn[2]};
+                const float rq = rn;
+                if (q + 1 < BQ) {
+                    xn[0] = msg[a0(q + 1)]; xn[1] = msg[a1(q + 1)]; xn[2] = msg[a2(q + 1)];
+                    rn = rsm[(q + 1) * NT + tid];
+                }
+                const float L = var_node_spa<DV>(x, DV, rq);
                 const bool b = (L <= 0.f);
                 const uint32_t tagbit = b ? tagmask : 0u;
                 msg[i0] = __uint_as_float(__float_as_uint(to_check_msg(x[0])) | tagbit);

@@ -81,6 +81,8 @@ struct ldpc535_code {
     uint16_t *d_w_chk_pos = nullptr, *d_w_var_pos = nullptr;   // warp kernel strip layout
     int32_t *d_w_pos_edge = nullptr;
     uint16_t *d_var_row4 = nullptr;   // [N][4] message addresses of a bit (regular codes, dv <= 4)
+    uint16_t *d_var_row4_rt = nullptr; // the same under the coloured-row layout of the register-table kernel
+    uint32_t *d_chk_color = nullptr;  // [M] colours of a storage column's six slots inside their rows: slot s at bits 5s+2 .. 5s+6
     unsigned int *d_cursor = nullptr; // window cursors of the register-table kernel (one per launch in flight, round-robin)
     unsigned int cursor_launch = 0;
     int c4_refill_min = 1;            // "c4-refill": lanes of a warp that must be waiting before its slots are refilled
@@ -210,6 +212,15 @@ int finish_create(ldpc535_code *c)
             for (int v = 0; v < t.N; v++)
                 for (int k = 0; k < t.dv_max; k++) row4[(size_t)v * 4 + k] = t.var_slot[(size_t)k * t.N + v];
             if ((st = upload(&c->d_var_row4, row4.data(), row4.size() * 2, row4.size() * 2))) return st;
+            if (!t.row_color.empty()) {
+                for (int v = 0; v < t.N; v++)
+                    for (int k = 0; k < t.dv_max; k++) row4[(size_t)v * 4 + k] = t.var_slot_colored[(size_t)k * t.N + v];
+                if ((st = upload(&c->d_var_row4_rt, row4.data(), row4.size() * 2, row4.size() * 2))) return st;
+                std::vector<uint32_t> cc(t.M, 0);
+                for (int j = 0; j < t.M; j++)
+                    for (int sl = 0; sl < 6; sl++) cc[j] |= (uint32_t)t.row_color[(size_t)j * 6 + sl] << (5 * sl + 2);
+                if ((st = upload(&c->d_chk_color, cc.data(), cc.size() * 4, cc.size() * 4))) return st;
+            }
             c->fits_regular = true;
         }
     }
@@ -261,7 +272,7 @@ void release(ldpc535_code *c)
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
-    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_cursor); cudaFree(c->d_select); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_var_row4_rt); cudaFree(c->d_chk_color); cudaFree(c->d_cursor); cudaFree(c->d_select); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
     delete c;
 }
 
@@ -418,7 +429,7 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
         // kernel with the tables in shared memory (kept for A/B measurements and other sizes)
         const bool fixed8k = c->t.M == 4096 && c->t.N == 8192 && c->block_threads == 1024;
         const int grid = (int)std::min<long long>(p.n_win, (long long)c->sm_count);
-        if (fixed8k && c->regular_variant == 1) {
+        if (fixed8k && c->regular_variant == 1 && c->d_chk_color) {
             if (!c->d_cursor && cudaMalloc(reinterpret_cast<void **>(&c->d_cursor), 64 * sizeof(unsigned int)) != cudaSuccess)
                 return fail(LDPC535_ERR_CUDA, "cursor allocation");
             p.cursor = c->d_cursor + (c->cursor_launch++ & 63u);          // zeroed on the stream just before its launch
@@ -428,7 +439,7 @@ int launch_decode(ldpc535_code *c, int forced, int method, bool dbg, DecodeParam
             const size_t smem = regular_rt_smem_bytes<6, 4096, 8192>();
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) {
-                kern<<<grid, 512, smem, st>>>(p, c->d_var_row4);
+                kern<<<grid, 512, smem, st>>>(p, c->d_var_row4_rt, c->d_chk_color);
                 e = cudaGetLastError();
             }
         } else {
