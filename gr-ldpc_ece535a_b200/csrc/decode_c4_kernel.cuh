@@ -123,7 +123,7 @@ constexpr int kCtasPerSm = C4_CTAS;
 constexpr int kChkGroup = C4_CHK_GROUP;     // checks between barriers
 constexpr int kVarGroup = C4_VAR_GROUP;     // variables between barriers
 #ifndef C4_REG_EDGES
-#define C4_REG_EDGES 100
+#define C4_REG_EDGES 106
 #endif
 #ifndef C4_GROUPS
 #define C4_GROUPS 1

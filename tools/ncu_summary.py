@@ -1,7 +1,12 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (first kernel) for profiles/: time, pipe utilisation, stall reasons,
-shared-memory wavefronts/conflicts, DRAM bytes.  Usage: ncu_summary.py file.ncu-rep"""
+shared-memory wavefronts/conflicts, DRAM bytes.  Usage: ncu_summary.py file.ncu-rep
+       ncu_summary.py file.ncu-rep --traffic <kernel key> <codewords in the captured launch>
+           also records dram bytes per codeword of that capture in profiles/ncu_traffic.json,
+           which bench.py reads for roofline.traffic (measured, not a literal)."""
 import csv
+import json
+import os
 import subprocess
 import sys
 
@@ -19,7 +24,7 @@ WANT = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "launch__grid_size",
         "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
 
 
-def main(path):
+def main(path, traffic=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -36,7 +41,26 @@ def main(path):
                 stalls.append((float(d[h]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
         print("  warp stalls per issued instruction (top):",
               ", ".join("%s %.2f" % (n, v) for v, n in sorted(stalls, reverse=True)[:8]))
+        if traffic:
+            key, n_cw = traffic[0], int(traffic[1])
+            def to_bytes(name):
+                mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u[name]]
+                return float(d[name]) * mult
+            total = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+            jp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+            try:
+                with open(jp) as f:
+                    doc = json.load(f)
+            except OSError:
+                doc = {"kernels": {}}
+            doc["kernels"][key] = {"dram_bytes_per_codeword": total / n_cw, "dram_bytes": total, "codewords": n_cw,
+                                   "source": "ncu --set full capture %s (dram__bytes_read.sum + dram__bytes_write.sum)"
+                                             % os.path.basename(path)}
+            with open(jp, "w") as f:
+                json.dump(doc, f, indent=1)
+            print("  -> %s: %.1f DRAM bytes per codeword" % (jp, total / n_cw))
+            traffic = None
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[3:5] if len(sys.argv) >= 5 and sys.argv[2] == "--traffic" else None)
