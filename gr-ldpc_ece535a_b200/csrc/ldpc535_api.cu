@@ -93,6 +93,12 @@ struct ldpc535_code {
     uint32_t *d_Pt = nullptr, *d_Pw = nullptr;
     uint32_t *d_m4r = nullptr;        // table of the look-up encoder (large codes), see encode_m4r_kernel.cuh
     bool use_m4r = true;              // LDPC535_ENCODER=generic switches it off (A/B measurements)
+    int m4r_ring = 60;                // look-up encoder variant (LDPC535_M4R_RING): 40 | 60 = free-running kernel with a 4- / 6-slot
+                                      // ring (60: default); 42 | 62 = barrier kernel, ring slots x stages per barrier
+    std::vector<std::pair<cudaStream_t, uint4 *>> m4r_parks;   // free-running kernel: parity scratch, one per stream in use
+    int m4r_tpf = 7;                  // free-running kernel: frames per slot, 7 | 8 (LDPC535_M4R_TPF; 8 spills)
+    int m4r_tile = 0;                 // frames per tile, 0 = balanced over the SMs (LDPC535_M4R_TILE)
+    uint32_t m4r_flags = 0;           // timing experiments (LDPC535_M4R_FLAGS, kM4rNo*): wrong results
     int tabA_bytes = 0, tabB_bytes = 0;
     int dc_t = 0, dv_t = 0;           // template sizes used (6/3 or 16/8), 0 = unsupported degrees
     bool fits_warp = false, fits_block = false, is_c4 = false;
@@ -192,9 +198,15 @@ int finish_create(ldpc535_code *c)
 
     // large codes: the look-up encoder's table, built on the device from the column masks
     if (const char *e = getenv("LDPC535_ENCODER")) c->use_m4r = strcmp(e, "generic") != 0;
+    if (const char *e = getenv("LDPC535_M4R_RING")) { const int r = atoi(e); if (r == 42 || r == 62 || r == 40 || r == 60) c->m4r_ring = r; }
+    if (const char *e = getenv("LDPC535_M4R_TPF")) c->m4r_tpf = atoi(e) == 8 ? 8 : 7;
+    if (const char *e = getenv("LDPC535_M4R_TILE")) c->m4r_tile = std::max(0, std::min(1024, atoi(e)));
+#ifdef LDPC535_TIMING_EXPERIMENTS      // builds under tools/ab/ only: parts of the kernel switched off, wrong results
+    if (const char *e = getenv("LDPC535_M4R_FLAGS")) c->m4r_flags = (uint32_t)atoi(e);
+#endif
     if (t.M % kM4rRows == 0 && t.K % 128 == 0 && t.M >= 4 * kM4rRows && (t.K / 32) % (t.M / kM4rRows) == 0 &&
         encode_m4r_table_bytes(t.M, t.K) <= ((size_t)512 << 20) &&
-        encode_m4r_smem_bytes<8>() <= c->smem_optin) {
+        encode_m4r_smem_bytes<8, 6>() <= c->smem_optin) {
         CU(cudaMalloc(reinterpret_cast<void **>(&c->d_m4r), encode_m4r_table_bytes(t.M, t.K)));
         encode_m4r_build_kernel<<<(t.M / kM4rRows) * (t.K / 8), 32>>>(c->d_Pt, c->d_m4r, t.M, t.K, t.mwords);
         CU(cudaGetLastError());
@@ -272,7 +284,7 @@ void release(ldpc535_code *c)
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
-    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); cudaFree(c->d_var_row4); cudaFree(c->d_var_row4_rt); cudaFree(c->d_chk_color); cudaFree(c->d_cursor); cudaFree(c->d_select); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
+    cudaFree(c->d_slot_edge); cudaFree(c->d_Pt); cudaFree(c->d_Pw); cudaFree(c->d_m4r); for (auto &pk : c->m4r_parks) cudaFree(pk.second); cudaFree(c->d_var_row4); cudaFree(c->d_var_row4_rt); cudaFree(c->d_chk_color); cudaFree(c->d_cursor); cudaFree(c->d_select); cudaFree(c->d_w_chk_pos); cudaFree(c->d_w_var_pos); cudaFree(c->d_w_pos_edge);
     delete c;
 }
 
@@ -521,15 +533,63 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
             const long long nf = std::min<long long>(chunk_max, (long long)n_frames - done);
             EncodeParams q = p;
             q.in = p.in + done * p.nbytes; q.out = p.out + done * t.N; q.n_frames = nf;
-            // frames per tile chosen so that every SM has units when the batch allows
-            auto units_of = [&](int f) { return ((nf + (long long)kM4rSlots * f - 1) / ((long long)kM4rSlots * f)) * rbs; };
-            const int tpf = units_of(8) >= 2 * sms ? 8 : units_of(4) >= 2 * sms ? 4 : units_of(2) >= sms ? 2 : 1;
-            void (*kern)(const EncodeParams, const uint4 *) =
-                tpf == 8 ? encode_m4r_kernel<8> : tpf == 4 ? encode_m4r_kernel<4> : tpf == 2 ? encode_m4r_kernel<2> : encode_m4r_kernel<1>;
-            const size_t smem = tpf == 8 ? encode_m4r_smem_bytes<8>() : tpf == 4 ? encode_m4r_smem_bytes<4>() : tpf == 2 ? encode_m4r_smem_bytes<2>() : encode_m4r_smem_bytes<1>();
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
-            kern<<<(int)std::min<long long>(units_of(tpf), sms), kM4rThreads, smem, st>>>(q, reinterpret_cast<const uint4 *>(c->d_m4r));
+            // Frames per tile: a unit costs a + b * frames / 128 (table stages of the row block, look-ups and
+            // stores of its frames; measured a : b = 2.85) and the slowest SM works on ceil(units / SMs) of
+            // them, so take the tile count that minimises ceil(tiles * RB / SMs) * (2.85 + frames / 128).
+            const bool fr = c->m4r_ring == 40 || c->m4r_ring == 60;
+            const int tpf = fr ? c->m4r_tpf : 8;
+            const long long slots = fr ? kM4rFrSlots : kM4rSlots, cap = slots * tpf;
+            long long tiles = (nf + cap - 1) / cap;
+            if (c->m4r_tile > 0) {
+                tiles = (nf + std::min<long long>(cap, c->m4r_tile) - 1) / std::min<long long>(cap, c->m4r_tile);
+            } else {
+                double best = 1e300;
+                for (long long nt = tiles, last = tiles + 2 * sms; nt <= last && nt <= nf; nt++) {
+                    const long long fr_t = (nf + nt - 1) / nt;
+                    const double cost = (double)((nt * rbs + sms - 1) / sms) * (2.85 + (double)fr_t / slots);
+                    if (cost < best - 1e-9) { best = cost; tiles = nt; }
+                }
+            }
+            M4rRun run;
+            run.tile_frames = (uint32_t)std::min<long long>(cap, (nf + tiles - 1) / tiles);
+            run.flags = c->m4r_flags;
+            const long long units = ((nf + run.tile_frames - 1) / run.tile_frames) * rbs;
+            const int grid = (int)std::min<long long>(units, sms);
+            cudaError_t e;
+            if (fr) {
+                uint4 *park = nullptr;
+                for (auto &pk : c->m4r_parks) if (pk.first == st) park = pk.second;
+                if (!park) {
+                    if (cudaMalloc(reinterpret_cast<void **>(&park), encode_m4r_fr_park_bytes((int)sms)) != cudaSuccess)
+                        return fail(LDPC535_ERR_CUDA, "look-up encoder scratch allocation");
+                    c->m4r_parks.emplace_back(st, park);
+                }
+                M4rFrRun fr_run;
+                fr_run.tile_frames = run.tile_frames; fr_run.n_frames = (uint32_t)nf; fr_run.n_units = (uint32_t)units;
+                fr_run.G = (uint32_t)(t.K / 8); fr_run.RB = (uint32_t)rbs;
+                fr_run.sys_words = (fr_run.G / fr_run.RB) >> 2; fr_run.n_pairs = fr_run.sys_words * tpf;
+                fr_run.in_wstride = (uint32_t)p.nbytes >> 2; fr_run.out_qstride = (uint32_t)t.N >> 1;
+                fr_run.in_tstride = fr_run.in_wstride * kM4rFrSlots; fr_run.out_tstride = fr_run.out_qstride * kM4rFrSlots;
+                fr_run.half_m = (uint32_t)t.M >> 1;
+                fr_run.grid_tiles = (uint32_t)grid / fr_run.RB; fr_run.grid_rbs = (uint32_t)grid % fr_run.RB;
+                fr_run.drain = fr_run.G >= 64u * tpf ? 1u : 0u;
+                void (*kern)(const uint32_t *, float4 *, const unsigned char *, const M4rFrRun, uint32_t *) =
+                    c->m4r_ring == 60 ? (tpf == 7 ? encode_m4r_fr_kernel<7, 6> : encode_m4r_fr_kernel<8, 6>)
+                                      : (tpf == 7 ? encode_m4r_fr_kernel<7, 4> : encode_m4r_fr_kernel<8, 4>);
+                const size_t smem = c->m4r_ring == 60 ? encode_m4r_fr_smem_bytes<8, 6>() : encode_m4r_fr_smem_bytes<8, 4>();
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                    return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
+                kern<<<grid, kM4rThreads, smem, st>>>(reinterpret_cast<const uint32_t *>(q.in), reinterpret_cast<float4 *>(q.out),
+                                                      reinterpret_cast<const unsigned char *>(c->d_m4r), fr_run,
+                                                      reinterpret_cast<uint32_t *>(park));
+            } else {
+                void (*kern)(const EncodeParams, const uint4 *, const M4rRun) =
+                    c->m4r_ring == 62 ? encode_m4r_kernel<8, 6, 2> : encode_m4r_kernel<8, 4, 2>;
+                const size_t smem = c->m4r_ring == 42 ? encode_m4r_smem_bytes<8, 4>() : encode_m4r_smem_bytes<8, 6>();
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                    return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
+                kern<<<grid, kM4rThreads, smem, st>>>(q, reinterpret_cast<const uint4 *>(c->d_m4r), run);
+            }
             if (done + chunk_max < (long long)n_frames) {
                 if ((e = cudaGetLastError()) != cudaSuccess) return fail(LDPC535_ERR_CUDA, std::string("encode launch: ") + cudaGetErrorString(e));
                 c->launches++;

@@ -420,33 +420,49 @@ def test_c8k_kernels_agree(c8k):
             assert np.array_equal(x, y)
 
 
-def test_c8k_lookup_encoder_equals_scan_encoder(c8k, monkeypatch):
-    """The table look-up encoder (encode_m4r_kernel, default for this size) against the AND/XOR scan
-    (encode_generic_kernel, LDPC535_ENCODER=generic): identical symbols for ragged batch sizes on
-    every tile shape (128, 256, 512, 1024 frames per CTA), device-resident for the large ones."""
+@pytest.mark.parametrize("variant", [None, "60/8", "40/7", "42", "62"])
+def test_c8k_lookup_encoder_equals_scan_encoder(c8k, monkeypatch, variant):
+    """The table look-up encoders (default for this size: the free-running encode_m4r_fr_kernel with a
+    6-slot ring and 7 frames per slot; LDPC535_M4R_RING / LDPC535_M4R_TPF select the 4-slot ring, 8
+    frames per slot and the barrier kernel encode_m4r_kernel) against the AND/XOR scan
+    (encode_generic_kernel, LDPC535_ENCODER=generic): identical symbols for ragged batch sizes --
+    partial tiles, tiles smaller than a CTA, fewer units than SMs, several units per CTA (the parked
+    parity of one unit drained during the next) -- device-resident for the large ones."""
     import torch
     monkeypatch.setenv("LDPC535_ENCODER", "generic")
     scan = L.Code(c8k.h_csr() + (c8k.M, c8k.N), device=0)
     monkeypatch.delenv("LDPC535_ENCODER")
+    if variant is None:
+        look = c8k
+    else:
+        ring, _, tpf = variant.partition("/")
+        monkeypatch.setenv("LDPC535_M4R_RING", ring)
+        if tpf:
+            monkeypatch.setenv("LDPC535_M4R_TPF", tpf)
+        look = L.Code(c8k.h_csr() + (c8k.M, c8k.N), device=0)
+        monkeypatch.delenv("LDPC535_M4R_RING")
+        monkeypatch.delenv("LDPC535_M4R_TPF", raising=False)
     rng = np.random.default_rng(18)
     for n in (1, 257, 3071, 3072, 3073, 4100):             # the look-up kernel takes over at 3072 frames
         data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
-        assert np.array_equal(c8k.encode(data), scan.encode(data)), n
+        assert np.array_equal(look.encode(data), scan.encode(data)), n
     sms = L.device_info(0)["sm_count"]
     gen = torch.Generator(device="cuda")
     gen.manual_seed(18)
-    for n in (sms * 32 * 2 + 37, sms * 64 * 4 + 1, sms * 64 * 8 + 129, sms * 128 * 8 + 5):
+    for n in (sms * 32 * 2 + 37, sms * 64 * 4 + 1, sms * 64 * 8 + 129, sms * 128 * 8 + 5, sms * 217 * 3 + 11):
         d = torch.randint(0, 256, (n, c8k.nbytes), dtype=torch.uint8, device="cuda", generator=gen)
         a = torch.empty((n, c8k.N, 2), dtype=torch.float32, device="cuda")
         b = torch.empty((n, c8k.N, 2), dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
-        c8k.encode_dev(d.data_ptr(), n, a.data_ptr())
+        look.encode_dev(d.data_ptr(), n, a.data_ptr())
         scan.encode_dev(d.data_ptr(), n, b.data_ptr())
-        c8k.sync()
+        look.sync()
         scan.sync()
         assert torch.equal(a, b), n
         del a, b, d
     scan.close()
+    if look is not c8k:
+        look.close()
 
 
 def test_c8k_regular_kernel_variants_agree(c8k, monkeypatch):

@@ -21,7 +21,15 @@ WANT = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "launch__grid_size",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+        "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__lsuin_requests.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__m_l1tex2xbar_write_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_global_st.sum"]
 
 
 def main(path, traffic=None):
