@@ -511,7 +511,7 @@ def run_gpu(args):
     if args.kernel:
         code.set_kernel(args.kernel)
     # the launcher knows how many ranks share the host: give each its share of the cores and let
-    # the handle decide pack-or-raw from that (>= 12 threads: pack) -- unless told otherwise
+    # the handle decide pack-or-raw chunk by chunk from its own measurements -- unless told otherwise
     share = max(1, min(cores_host // local_world, len(os.sched_getaffinity(0))))
     code.set_host_path(args.pack_pinned, args.pack_threads or share)
     stream = torch.cuda.Stream()            # a real stream: NULL would mean "the handle's own"
@@ -618,6 +618,7 @@ def run_gpu(args):
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_pass()
+    hs0 = code.host_stats()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -627,9 +628,14 @@ def run_gpu(args):
     e2e_value = e2e_cw * world * e2e_steps * K_INFO / (e2e_ms * 1e-3) / 1e9
     e2e_same = bool(np.array_equal(h_bytes, d_bytes[:e2e_cw].cpu().numpy()))
     hp = code.host_path()
-    host_path = ("%d host threads pack the real parts into pinned staging (halves PCIe bytes)" % hp["pack_threads"]
-                 if hp["pack_pinned"] else "copy engine reads the caller's pinned buffer directly")
-    pcie_bytes = e2e_cw * world * (256 if hp["pack_pinned"] else 512)
+    hs1 = code.host_stats()
+    n_packed, n_raw = hs1["chunks_packed"] - hs0["chunks_packed"], hs1["chunks_raw"] - hs0["chunks_raw"]
+    host_path = {0: "copy engine reads the caller's pinned buffer directly",
+                 1: "%d host threads pack the real parts into pinned staging (halves PCIe bytes)" % hp["pack_threads"],
+                 2: "measured: %d host threads pack the real parts of a 128 MiB chunk into pinned staging while they do a byte "
+                    "faster than the copy engine, otherwise it reads the caller's pinned buffer directly (rank 0 in the "
+                    "timed passes: %d chunks packed, %d raw)" % (hp["pack_threads"], n_packed, n_raw)}[hp["pack_pinned"]]
+    pcie_bytes = (hs1["h2d_bytes"] - hs0["h2d_bytes"]) // e2e_steps * world      # rank 0's mix, every rank
 
     # ---- the box's host->device ceiling with every rank copying at once: plain pinned copies of the
     # same buffer in the pipeline's chunk size, no kernel, no packing ----

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,7 +52,8 @@ enum KernelFamily { kAuto = 0, kWarp = 1, kBlock = 2, kC4Thread = 3, kRegular = 
 
 constexpr int kSlots = 3;                       // pipeline depth of the host-buffer API
 constexpr size_t kChunkSymBytes = 128u << 20;   // symbol bytes staged per slot (upper bound; slots grow on demand)
-constexpr int kPackPinnedMinThreads = 12;       // pinned input is packed by the host from this many threads on
+constexpr int kPackAdaptive = 2;                // pack_pinned: 0 never, 1 always, 2 chunk by chunk (default)
+constexpr int kH2dRing = 8;                     // timing events of the last chunks' host-to-device copies
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -109,11 +111,18 @@ struct ldpc535_code {
     cudaStream_t stream = nullptr;
     // host-API pipeline
     int pack_threads = 1;
-    int pack_pinned = 0;          // pack even when the caller's buffer is pinned.  Default: when this handle
-                                  // has >= 12 packing threads (ldpc535_code_set_host_path / LDPC535_PACK_PINNED
-                                  // override).  Measured per 5.12 GB on B200 boxes: one GPU, 16 cores: 8 threads
-                                  // 89 ms, 12+ threads 76 ms, raw PCIe 94 ms; four ranks with 8 cores each:
-                                  // packing 220 ms (host memory traffic doubles), raw PCIe 101 ms.
+    int pack_pinned = kPackAdaptive;  // what happens to PINNED input (pageable input is always packed through staging):
+                                  // 0 the copy engine reads it as it is (8 bytes per symbol over PCIe), 1 the host team packs
+                                  // the real parts first (4 bytes per symbol, but 12 bytes of host memory traffic), 2 decided
+                                  // from the measured rates of the team and of the copy engine.  Measured per 5.12 GB on B200
+                                  // boxes: one rank, 16 threads: packed 70 ms, raw 94 ms; two ranks, 12 threads each: packed
+                                  // 109 ms, raw 94 ms; four ranks, 8 threads each: packed 220 ms, raw 101 ms.
+    double pack_ns_per_byte = 0, h2d_ns_per_byte = 0;      // running estimates (input bytes packed / bytes copied), 0 = not measured yet
+    cudaEvent_t h2d_t0[kH2dRing] = {}, h2d_t1[kH2dRing] = {};
+    size_t h2d_len[kH2dRing] = {};                          // bytes of the copy of chunk k % kH2dRing, 0 = none
+    bool h2d_alone[kH2dRing] = {};                          // no earlier copy was pending when it was issued
+    uint64_t chunks_packed = 0, chunks_raw = 0, h2d_bytes = 0, host_calls = 0;
+    bool packing = false;                                   // current regime of the measured mode
     PackPool *pool = nullptr;     // persistent packing team, created on first use
     size_t max_win_per_chunk = 0;
     Slot slots[kSlots];
@@ -162,8 +171,7 @@ int finish_create(ldpc535_code *c)
                                                std::to_string(prop.minor) + ", kernels are built for sm_100a");
     c->sm_count = prop.multiProcessorCount;
     c->pack_threads = default_pack_threads();
-    c->pack_pinned = c->pack_threads >= kPackPinnedMinThreads;
-    if (const char *e = getenv("LDPC535_PACK_PINNED")) c->pack_pinned = atoi(e) != 0;
+    if (const char *e = getenv("LDPC535_PACK_PINNED")) c->pack_pinned = std::max(0, std::min(2, atoi(e)));
     c->smem_optin = prop.sharedMemPerBlockOptin;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
@@ -281,6 +289,10 @@ void release(ldpc535_code *c)
         if (s.h_stage) cudaFreeHost(s.h_stage);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (int i = 0; i < kH2dRing; i++) {
+        if (c->h2d_t0[i]) cudaEventDestroy(c->h2d_t0[i]);
+        if (c->h2d_t1[i]) cudaEventDestroy(c->h2d_t1[i]);
     }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->d_chk_var); cudaFree(c->d_var_slot); cudaFree(c->d_chk_deg);
@@ -626,6 +638,10 @@ int ensure_slots(ldpc535_code *c)
         if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
+    for (int i = 0; i < kH2dRing; i++) {
+        if (!c->h2d_t0[i]) CU(cudaEventCreate(&c->h2d_t0[i]));
+        if (!c->h2d_t1[i]) CU(cudaEventCreate(&c->h2d_t1[i]));
+    }
     return LDPC535_OK;
 }
 
@@ -900,6 +916,15 @@ int ldpc535_code_host_path(const ldpc535_code *c, int *pack_pinned, int *pack_th
     return LDPC535_OK;
 }
 
+int ldpc535_code_host_stats(const ldpc535_code *c, uint64_t *chunks_packed, uint64_t *chunks_raw, uint64_t *h2d_bytes)
+{
+    if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
+    if (chunks_packed) *chunks_packed = c->chunks_packed;
+    if (chunks_raw) *chunks_raw = c->chunks_raw;
+    if (h2d_bytes) *h2d_bytes = c->h2d_bytes;
+    return LDPC535_OK;
+}
+
 int ldpc535_code_set_host_path(ldpc535_code *c, int pack_pinned, int pack_threads)
 {
     if (!c) return fail(LDPC535_ERR_INVALID, "code is NULL");
@@ -909,7 +934,9 @@ int ldpc535_code_set_host_path(ldpc535_code *c, int pack_pinned, int pack_thread
         delete c->pool;                     // the team is re-created with the new size on next use
         c->pool = nullptr;
     }
-    c->pack_pinned = pack_pinned < 0 ? (c->pack_threads >= kPackPinnedMinThreads) : (pack_pinned != 0);
+    if (pack_pinned > 2) return fail(LDPC535_ERR_INVALID, "pack_pinned must be -1 (default), 0, 1 or 2");
+    c->pack_pinned = pack_pinned < 0 ? kPackAdaptive : pack_pinned;
+    c->pack_ns_per_byte = 0;                // measured again with the new team
     return LDPC535_OK;
 }
 
@@ -1137,11 +1164,13 @@ int ldpc535_decode_batch(ldpc535_code *c, const float *sym, size_t n_sym, const 
     // Pageable input (a GNU Radio buffer) must be staged through pinned memory anyway: stage only
     // the real parts.  Pinned input goes to the copy engine as it is unless the handle packs pinned
     // input too (ldpc535_code_set_host_path).
-    const bool pack = n_win && (!host_pointer_is_pinned(sym) || c->pack_pinned);
-    if (pack && !c->pool) {
+    const int pack_mode = !n_win ? 0 : !host_pointer_is_pinned(sym) ? 1 : c->pack_pinned;
+    if (pack_mode && !c->pool) {
         c->pool = new (std::nothrow) PackPool(c->pack_threads);
         if (!c->pool) return fail(LDPC535_ERR_NOMEM, "out of host memory");
     }
+    for (int i = 0; i < kH2dRing; i++) c->h2d_len[i] = 0;   // events of an earlier call say nothing about this one's queue
+    c->host_calls++;
     const size_t max_sym = kChunkSymBytes / 8;     // symbols per staging buffer
     size_t done = 0;
     int k = 0;
@@ -1165,17 +1194,60 @@ int ldpc535_decode_batch(ldpc535_code *c, const float *sym, size_t n_sym, const 
             }
             sym_lo = lo; sym_hi = hi;
         }
-        if ((st = slot_reserve(c, s, (sym_hi - sym_lo) * (pack ? 4 : 8), n, pack ? (sym_hi - sym_lo) * 4 : 0))) return st;
+        // the copy of chunk k - kSlots (this slot's previous one) is over: its time per byte, if it had the copy
+        // engines to itself (issued with no earlier copy pending -- two engines share the link, and a queued copy's
+        // start event fires long before its first byte moves)
+        const int ring = k % kH2dRing;
+        if (k >= kSlots) {
+            const int j = (k - kSlots) % kH2dRing;
+            float ms = 0.f;
+            if (c->h2d_len[j] && c->h2d_alone[j] && cudaEventElapsedTime(&ms, c->h2d_t0[j], c->h2d_t1[j]) == cudaSuccess && ms > 0.f) {
+                const double v = (double)ms * 1e6 / (double)c->h2d_len[j];
+                c->h2d_ns_per_byte = c->h2d_ns_per_byte > 0 ? 0.5 * c->h2d_ns_per_byte + 0.5 * v : v;
+            }
+            cudaGetLastError();
+        }
+        bool alone = true;
+        for (int b = 1; b < kSlots && b <= k; b++) {
+            const int j = (k - b) % kH2dRing;
+            if (c->h2d_len[j] && cudaEventQuery(c->h2d_t1[j]) == cudaErrorNotReady) alone = false;
+        }
+        cudaGetLastError();
+        c->h2d_alone[ring] = alone;
+        const size_t span = sym_hi - sym_lo;
+        bool pack = pack_mode == 1;
+        if (pack_mode == kPackAdaptive) {
+            // Packing S symbols holds this thread for 8 S p and leaves a 4 S h copy; the raw copy takes 8 S h (p, h =
+            // measured ns per byte of the team and of the copy engine): packing wins when p < h.  One regime at a
+            // time, with hysteresis -- mixing the two was measured and loses: packing only the chunks that fit under
+            // the copies already queued moved 20 % fewer PCIe bytes in the same time with two ranks on a 24-core
+            // host (both paths share the host's memory system), and flipping between the regimes chunk by chunk
+            // was slower than either.  While the input goes raw, the second chunk of every 8th call is packed to
+            // keep p current.
+            if (c->pack_ns_per_byte <= 0 || (!c->packing && (c->host_calls & 7u) == 0)) pack = k == 1;
+            if (c->pack_ns_per_byte > 0 && c->h2d_ns_per_byte > 0) {
+                c->packing = c->pack_ns_per_byte * (c->packing ? 1.05 : 1.25) < c->h2d_ns_per_byte;
+                pack = pack || c->packing;
+            }
+        }
+        if ((st = slot_reserve(c, s, span * (pack ? 4 : 8), n, pack ? span * 4 : 0))) return st;
         if (win_offset) {
             for (size_t i = 0; i < n; i++) s.h_off[i] = (long long)((size_t)win_offset[done + i] - sym_lo);
             CU(cudaMemcpyAsync(s.d_off, s.h_off, n * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
         }
         if (pack) {
-            c->pool->pack(sym + sym_lo * 2, s.h_stage, sym_hi - sym_lo);
-            CU(cudaMemcpyAsync(s.d_sym, s.h_stage, (sym_hi - sym_lo) * 4, cudaMemcpyHostToDevice, s.stream));
-        } else {
-            CU(cudaMemcpyAsync(s.d_sym, sym + sym_lo * 2, (sym_hi - sym_lo) * 8, cudaMemcpyHostToDevice, s.stream));
+            const auto t0 = std::chrono::steady_clock::now();
+            c->pool->pack(sym + sym_lo * 2, s.h_stage, span);
+            const double v = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / ((double)span * 8.0);
+            c->pack_ns_per_byte = c->pack_ns_per_byte > 0 ? 0.75 * c->pack_ns_per_byte + 0.25 * v : v;
         }
+        const void *h2d_src = pack ? static_cast<const void *>(s.h_stage) : static_cast<const void *>(sym + sym_lo * 2);
+        c->h2d_len[ring] = span * (pack ? 4 : 8);
+        CU(cudaEventRecord(c->h2d_t0[ring], s.stream));
+        CU(cudaMemcpyAsync(s.d_sym, h2d_src, c->h2d_len[ring], cudaMemcpyHostToDevice, s.stream));
+        CU(cudaEventRecord(c->h2d_t1[ring], s.stream));
+        c->h2d_bytes += c->h2d_len[ring];
+        (pack ? c->chunks_packed : c->chunks_raw)++;
         if (polarity)
             CU(cudaMemcpyAsync(s.d_pol, polarity + done, n, cudaMemcpyHostToDevice, s.stream));
         DecodeParams p = {};

@@ -43,6 +43,7 @@ SYMBOLS = {
     "ldpc535_pool_encode_batch": (_i, [_vp, _vp, _sz, _vp]),
     "ldpc535_code_host_path": (_i, [_vp, _pi, _pi]),
     "ldpc535_code_set_host_path": (_i, [_vp, _i, _i]),
+    "ldpc535_code_host_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "ldpc535_synth_bytes_dev": (_i, [_vp, _u64, _u64, _sz, _vp, _vp]),
     "ldpc535_synth_awgn_dev": (_i, [_vp, _u64, _u64, _sz, C.c_float, _vp, _vp]),
     "ldpc535_probe_pipe_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),

@@ -88,13 +88,19 @@ class Code:
               "set_kernel")
 
     def host_path(self):
-        """How decode() moves host symbols: {'pack_pinned': bool, 'pack_threads': int}."""
+        """How decode() moves host symbols: {'pack_pinned': 0 raw | 1 packed | 2 chunk by chunk, 'pack_threads': int}."""
         a, b = C.c_int(), C.c_int()
         check(lib().ldpc535_code_host_path(self._h, a, b), "host_path")
-        return {"pack_pinned": bool(a.value), "pack_threads": b.value}
+        return {"pack_pinned": a.value, "pack_threads": b.value}
+
+    def host_stats(self):
+        """Cumulative {'chunks_packed', 'chunks_raw', 'h2d_bytes'} of decode() on this handle."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().ldpc535_code_host_stats(self._h, a, b, c), "host_stats")
+        return {"chunks_packed": a.value, "chunks_raw": b.value, "h2d_bytes": c.value}
 
     def set_host_path(self, pack_pinned=-1, pack_threads=0):
-        """pack_threads >= 1 (0 keeps it); pack_pinned 0 / 1, or -1 to derive it from the team size."""
+        """pack_threads >= 1 (0 keeps it); pack_pinned 0 raw / 1 packed / 2 chunk by chunk, -1 = default (2)."""
         check(lib().ldpc535_code_set_host_path(self._h, int(pack_pinned), int(pack_threads)), "set_host_path")
 
     def launch_count(self):

@@ -208,15 +208,21 @@ LDPC535_API int ldpc535_code_set_kernel(ldpc535_code *code, const char *kernel);
 
 /* How ldpc535_decode_batch moves host symbols to the device.  Pageable input is always staged
  * through pinned memory by a persistent team of `pack_threads` host threads that copy only the
- * REAL parts (the decoder never reads the imaginary ones), halving the PCIe bytes; *pack_pinned
- * != 0 means pinned input is packed the same way instead of being handed to the copy engine as
- * it is.  Defaults: pack_threads = the cores this process may run on (at most 32), pack_pinned =
- * (pack_threads >= 12) -- with fewer threads per GPU the host memory traffic of packing costs more
- * than the PCIe bytes it saves. */
+ * REAL parts (the decoder never reads the imaginary ones), halving the PCIe bytes.  For PINNED
+ * input *pack_pinned says: 0 = the copy engine reads the caller's buffer as it is, 1 = the team
+ * packs it the same way first, 2 (default) = decided from running measurements of the team's and
+ * the copy engine's rates: chunks are packed while the team packs a byte faster than the copy
+ * engine moves one (packing costs 12 bytes of host memory traffic per symbol to save 4 on PCIe: it
+ * pays with many cores per GPU and not with few).  Default pack_threads = the cores this process
+ * may run on (at most 32). */
 LDPC535_API int ldpc535_code_host_path(const ldpc535_code *code, int *pack_pinned, int *pack_threads);
+/* What the host path has done so far on this handle: 128 MiB chunks packed / handed over as they
+ * were, and the bytes copied host -> device for symbols. */
+LDPC535_API int ldpc535_code_host_stats(const ldpc535_code *code, uint64_t *chunks_packed, uint64_t *chunks_raw,
+                                        uint64_t *h2d_bytes);
 /* Override them, e.g. from a launcher that runs one process per GPU and knows how many host cores
- * each process gets: pack_threads >= 1 (0 keeps the current team size); pack_pinned 0 / 1, or -1
- * to re-derive it from the team size.  The library itself reads no launcher environment. */
+ * each process gets: pack_threads >= 1 (0 keeps the current team size); pack_pinned 0 / 1 / 2, or
+ * -1 for the default.  The library itself reads no launcher environment. */
 LDPC535_API int ldpc535_code_set_host_path(ldpc535_code *code, int pack_pinned, int pack_threads);
 
 /* ---- several GPUs from one host process -------------------------------------- */
