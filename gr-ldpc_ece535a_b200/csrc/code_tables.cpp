@@ -313,6 +313,25 @@ void color_warp_layout(CodeTables &t)
             const int e = t.edge_of_col[q];
             t.w_var_pos[(size_t)k * 64 + c] = (uint16_t)(eu[e] * 32 + color[e]);
         }
+    // unused bit slots (bit degree <= k, or no such bit): 0x8000 | a bank that the real edges of the
+    // access (t, k) = bits 32 t .. 32 t + 31, edge k leave free -- the kernel reads its zero row and
+    // writes its dummy row there
+    for (int k = 0; k < DV; k++)
+        for (int tt = 0; tt < 2; tt++) {
+            std::vector<char> used(32, 0);
+            for (int l = 0; l < 32; l++) {
+                const uint16_t pos = t.w_var_pos[(size_t)k * 64 + 32 * tt + l];
+                if (pos != 0xFFFF) used[pos & 31] = 1;
+            }
+            int nb = 0;
+            for (int l = 0; l < 32; l++) {
+                uint16_t &pos = t.w_var_pos[(size_t)k * 64 + 32 * tt + l];
+                if (pos != 0xFFFF) continue;
+                while (used[nb]) nb++;
+                pos = (uint16_t)(0x8000u | (unsigned)nb);
+                used[nb] = 1;
+            }
+        }
 }
 
 }  // namespace

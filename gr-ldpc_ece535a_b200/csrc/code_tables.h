@@ -44,7 +44,7 @@ struct CodeTables {
     std::vector<uint16_t> var_slot_colored;   // [dv_max][N]  message index under that layout
     // warp-per-codeword kernel (M <= 32, N <= 64): conflict-free shared-memory strip layout
     std::vector<uint16_t> w_chk_pos;    // [dc_max][32]  position of (slot s, check lane), padded slots included
-    std::vector<uint16_t> w_var_pos;    // [dv_max][64]  position of the k-th edge of a bit, or 0xFFFF
+    std::vector<uint16_t> w_var_pos;    // [dv_max][64]  position of the k-th edge of a bit, or 0x8000 | a bank free in that access
     std::vector<int32_t> w_pos_edge;    // [dc_max*32]   position -> CSR edge id or -1 (message dumps)
     std::vector<uint8_t> chk_deg;       // [M]
     std::vector<uint8_t> var_deg;       // [N]

@@ -143,11 +143,25 @@ decode_warp_kernel(const DecodeParams p)
     if (p.select && *p.select != p.select_want) return;      // the other family was picked for these windows
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // strip of this warp: DC rows of 32 messages (layout: code_tables.cpp color_warp_layout), one row
-    // of per-lane dummies (writes of unused slots) and a row holding the two constants unused
-    // slots read: [0] the check update's identity, [1] zero
-    T *msg = reinterpret_cast<T *>(smem_w) + warp * ((DC + 2) * 32);
-    constexpr int kDummy = DC * 32, kPadWord = (DC + 1) * 32, kZeroWord = (DC + 1) * 32 + 1;
+    // Strip of this warp (layout: code_tables.cpp color_warp_layout): DC rows of 32 messages, one row
+    // of dummies (writes of unused slots), one row holding the check update's identity and one row of
+    // zeros (what unused check / bit slots read).  An unused slot reads and writes the word of ITS row
+    // in a bank the access's real edges leave free, so every access of the loop is one wavefront
+    // (round 1 read a single identity / zero word: a 2-way conflict on almost every access of the
+    // shipped code, whose degrees are uneven).  fp64 messages (min-sum) are kept as two planes of
+    // 32-bit words, low halves then high halves: an 8-byte word per lane made every access 4
+    // wavefronts with the 32-bank colouring, two 4-byte accesses are 2.
+    constexpr int kRows = DC + 3, kDummy = DC * 32, kPadRow = (DC + 1) * 32, kZeroRow = (DC + 2) * 32;
+    constexpr bool k64 = sizeof(T) == 8;
+    uint32_t *strip = reinterpret_cast<uint32_t *>(smem_w) + warp * ((k64 ? 2 : 1) * kRows * 32);
+    auto ld = [&](int pos) -> T {
+        if constexpr (k64) return (T)__hiloint2double((int)strip[kRows * 32 + pos], (int)strip[pos]);
+        else return (T)__uint_as_float(strip[pos]);
+    };
+    auto st = [&](int pos, T v) {
+        if constexpr (k64) { strip[pos] = (uint32_t)__double2loint((double)v); strip[kRows * 32 + pos] = (uint32_t)__double2hiint((double)v); }
+        else strip[pos] = __float_as_uint((float)v);
+    };
     const int M = p.M, N = p.N;
 
     // ---- this lane's rows/columns of H (loop invariant, registers) ----
@@ -170,27 +184,28 @@ decode_warp_kernel(const DecodeParams p)
 #pragma unroll
         for (int k = 0; k < DV; k++) {
             const int idx = (v < N) ? p.var_slot[k * N + v] : 0xFFFF;
-            vpos[t][k] = 0; vchk[t][k] = 0;
+            vpos[t][k] = p.w_var_pos[k * 64 + v];       // real edge: strip position; unused slot: 0x8000 | free bank
+            vchk[t][k] = 0;
             if (idx != 0xFFFF) {
                 vchk[t][k] = idx % M;
-                vpos[t][k] = p.w_var_pos[k * 64 + v];
                 vdeg[t] = k + 1;
             }
         }
     }
-    // Unused slots cost no predicates in the loop: a padded check slot READS the identity word and
-    // writes its own (never read) position; an unused bit slot reads zero and writes the lane's dummy.
+    // Unused slots cost no predicates in the loop: a padded check slot READS the identity row and
+    // writes its own (never read) position; an unused bit slot reads the zero row and writes the dummy row.
     int crd[DC], vrd[2][DV], vwr[2][DV];
 #pragma unroll
-    for (int s = 0; s < DC; s++) crd[s] = (s < cdeg) ? cpos[s] : kPadWord;
+    for (int s = 0; s < DC; s++) crd[s] = (s < cdeg) ? cpos[s] : kPadRow + (cpos[s] & 31);
 #pragma unroll
     for (int t = 0; t < 2; t++)
 #pragma unroll
         for (int k = 0; k < DV; k++) {
-            vrd[t][k] = (k < vdeg[t]) ? vpos[t][k] : kZeroWord;
-            vwr[t][k] = (k < vdeg[t]) ? vpos[t][k] : kDummy + lane;
+            vrd[t][k] = (k < vdeg[t]) ? vpos[t][k] : kZeroRow + (vpos[t][k] & 31);
+            vwr[t][k] = (k < vdeg[t]) ? vpos[t][k] : kDummy + (vpos[t][k] & 31);
         }
-    if (lane == 0) { msg[kPadWord] = pad_msg<METHOD, T>(); msg[kZeroWord] = (T)0; }
+    st(kPadRow + lane, pad_msg<METHOD, T>());
+    st(kZeroRow + lane, (T)0);
     __syncwarp();
 
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
@@ -198,7 +213,7 @@ decode_warp_kernel(const DecodeParams p)
     // warp (no registers held across the iterations): a warp that loaded and then used them sat out
     // the whole HBM latency once per codeword -- a fifth of all warp samples at 5 iterations (ncu,
     // profiles/r2c_*).
-    float *stage = reinterpret_cast<float *>(smem_w + sizeof(T) * (blockDim.x >> 5) * ((DC + 2) * 32)) + warp * 64;
+    float *stage = reinterpret_cast<float *>(smem_w + sizeof(T) * (blockDim.x >> 5) * (kRows * 32)) + warp * 64;
     auto fetch_window = [&](long long wq) {
         if (wq < p.n_win) {
             const long long offq = p.win_offset ? p.win_offset[wq] : wq * (long long)N;
@@ -271,14 +286,14 @@ decode_warp_kernel(const DecodeParams p)
                     if (k < vdeg[t]) {
                         if (DEBUG && p.dbgS)
                             p.dbgS[w * p.E + p.w_pos_edge[vpos[t][k]]] = (float)r[t] * kOut;
-                        msg[vpos[t][k]] = enc_msg<METHOD, T>(r[t]);
+                        st(vpos[t][k], enc_msg<METHOD, T>(r[t]));
                     }
             iters = p.max_iters;
             for (int h = 0; h < p.max_iters; h++) {
                 __syncwarp();
                 T m[DC];
 #pragma unroll
-                for (int s = 0; s < DC; s++) m[s] = msg[crd[s]];
+                for (int s = 0; s < DC; s++) m[s] = ld(crd[s]);
                 if (DEBUG && p.dbgM && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
@@ -289,7 +304,7 @@ decode_warp_kernel(const DecodeParams p)
                 }
                 if constexpr (METHOD == kMethodSpa) check_node_spa<DC>(m); else check_node_minsum<DC, T>(m);
 #pragma unroll
-                for (int s = 0; s < DC; s++) msg[cpos[s]] = m[s];
+                for (int s = 0; s < DC; s++) st(cpos[s], m[s]);
                 if (DEBUG && p.dbgE && lane < M) {
 #pragma unroll
                     for (int s = 0; s < DC; s++)
@@ -300,7 +315,7 @@ decode_warp_kernel(const DecodeParams p)
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
 #pragma unroll
-                    for (int k = 0; k < DV; k++) x[t][k] = msg[vrd[t][k]];
+                    for (int k = 0; k < DV; k++) x[t][k] = ld(vrd[t][k]);
                     if constexpr (METHOD == kMethodSpa) L[t] = var_node_spa_rk<DV>(x[t], rk[t]);
                     else L[t] = var_node_minsum<DV, T>(x[t], DV, r[t]);
                 }
@@ -325,7 +340,7 @@ decode_warp_kernel(const DecodeParams p)
                     {
                         if (DEBUG && p.dbgS && k < vdeg[t])
                             p.dbgS[w * p.E + p.w_pos_edge[vpos[t][k]]] = (float)x[t][k] * kOut;
-                        msg[vwr[t][k]] = enc_msg<METHOD, T>(x[t][k]);
+                        st(vwr[t][k], enc_msg<METHOD, T>(x[t][k]));
                     }
             }
             // dbgM so far holds the M that ENTERED the last check step -- what the reference

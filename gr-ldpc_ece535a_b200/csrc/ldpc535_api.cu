@@ -247,7 +247,8 @@ int finish_create(ldpc535_code *c)
     c->fits_warp = (t.M <= 32 && t.N <= 64);
     if (c->fits_warp) {
         // padded to the template slot counts (rows beyond dc_max / dv_max are never used)
-        std::vector<uint16_t> cp((size_t)c->dc_t * 32, 0), vp((size_t)c->dv_t * 64, 0xFFFF);
+        std::vector<uint16_t> cp((size_t)c->dc_t * 32, 0), vp((size_t)c->dv_t * 64, 0);
+        for (size_t i = 0; i < vp.size(); i++) vp[i] = (uint16_t)(0x8000u | (i & 31u));    // slots beyond dv_max: unused, own bank
         std::vector<int32_t> pe((size_t)c->dc_t * 32, -1);
         std::copy(t.w_chk_pos.begin(), t.w_chk_pos.end(), cp.begin());
         std::copy(t.w_var_pos.begin(), t.w_var_pos.end(), vp.begin());
@@ -365,7 +366,7 @@ template <int METHOD, int DC, int DV, bool DBG>
 cudaError_t launch_warp(const ldpc535_code *c, const DecodeParams &p, cudaStream_t st)
 {
     const int wpb = kWarpKernelThreads / 32;
-    const size_t smem = sizeof(msg_t<METHOD>) * wpb * (DC + 2) * 32 + sizeof(float) * wpb * 64;   // + symbol staging
+    const size_t smem = sizeof(msg_t<METHOD>) * wpb * (DC + 3) * 32 + sizeof(float) * wpb * 64;   // + symbol staging
     long long blocks = (p.n_win + wpb - 1) / wpb;
     auto kern = decode_warp_kernel<METHOD, DC, DV, DBG>;
     int per_sm = 8;                        // grid = the resident CTAs: one wave of persistent warps
