@@ -124,24 +124,63 @@ __device__ __forceinline__ uint32_t check_node_spa(float (&m)[DC])
 // sign, all exactly rounded in IEEE arithmetic and kept in the reference's order, so the
 // messages -- not just the decisions -- equal the reference's bit for bit at any iteration
 // count.  (An fp32 min-sum drifts on non-converging frames after a few dozen iterations.)
+//
+// How it is evaluated (round 2; the first version tracked the two smallest magnitudes and their
+// position and multiplied by an integer sign: 150 of the warp kernel's 263 instructions per
+// iteration, and that kernel is bound by instruction issue).  "All but one" minima come from
+// prefix / suffix minima, like the products of the sum-product update: 3 (DC - 2) two-way minima
+// and no position bookkeeping.  Signs are handled on the high words: the sign of the product of
+// the OTHER inputs is the XOR of all sign bits and the own one.  sign(0) = 0 makes the reference's
+// product over ALL inputs vanish as soon as one input is zero, and then every output of the check
+// is zero: one test of the overall minimum, applied as a mask.  Values are exactly the reference's
+// (a minimum of the same doubles, a sign flip); a zero result is +0 where the reference computes
+// 0 * min = +0 as well.
 template <int DC, typename T>
 __device__ __forceinline__ void check_node_minsum(T (&m)[DC])
 {
-    T min1 = (T)__int_as_float(0x7f800000), min2 = min1;   // two smallest magnitudes
-    int arg1 = -1;
-    int prod = 1;
+    static_assert(DC >= 2, "needs two slots");
+    if constexpr (sizeof(T) == 8) {
+        double a[DC];
+        uint32_t sx = 0;
 #pragma unroll
-    for (int s = 0; s < DC; s++) {
-        const T a = m[s] < (T)0 ? -m[s] : m[s];
-        prod *= (m[s] > (T)0) - (m[s] < (T)0);
-        if (a < min1) { min2 = min1; min1 = a; arg1 = s; }
-        else if (a < min2) { min2 = a; }
-    }
+        for (int s = 0; s < DC; s++) {
+            const uint32_t hi = (uint32_t)__double2hiint((double)m[s]);
+            sx ^= hi;
+            a[s] = __hiloint2double((int)(hi & 0x7fffffffu), __double2loint((double)m[s]));
+        }
+        auto mn2 = [](double x, double y) { return x < y ? x : y; };
+        double pre[DC], suf[DC];            // pre[s] = min over slots < s, suf[s] = min over slots > s
+        pre[1] = a[0];
 #pragma unroll
-    for (int s = 0; s < DC; s++) {
-        const int sg = prod * ((m[s] > (T)0) - (m[s] < (T)0));
-        const T mn = (s == arg1) ? min2 : min1;
-        m[s] = (T)sg * mn;
+        for (int s = 2; s < DC; s++) pre[s] = mn2(pre[s - 1], a[s - 1]);
+        suf[DC - 2] = a[DC - 1];
+#pragma unroll
+        for (int s = DC - 3; s >= 0; s--) suf[s] = mn2(suf[s + 1], a[s + 1]);
+        const bool anyzero = mn2(pre[DC - 1], a[DC - 1]) == 0.0;
+        const uint32_t zmask = anyzero ? 0u : 0xffffffffu, smask = anyzero ? 0u : 0x80000000u;
+#pragma unroll
+        for (int s = 0; s < DC; s++) {
+            const double mn = s == 0 ? suf[0] : s == DC - 1 ? pre[DC - 1] : mn2(pre[s], suf[s]);
+            const uint32_t hi = ((uint32_t)__double2hiint(mn) & zmask) | ((sx ^ (uint32_t)__double2hiint((double)m[s])) & smask);
+            m[s] = (T)__hiloint2double((int)hi, (int)((uint32_t)__double2loint(mn) & zmask));
+        }
+    } else {
+        T min1 = (T)__int_as_float(0x7f800000), min2 = min1;   // two smallest magnitudes
+        int arg1 = -1;
+        int prod = 1;
+#pragma unroll
+        for (int s = 0; s < DC; s++) {
+            const T a = m[s] < (T)0 ? -m[s] : m[s];
+            prod *= (m[s] > (T)0) - (m[s] < (T)0);
+            if (a < min1) { min2 = min1; min1 = a; arg1 = s; }
+            else if (a < min2) { min2 = a; }
+        }
+#pragma unroll
+        for (int s = 0; s < DC; s++) {
+            const int sg = prod * ((m[s] > (T)0) - (m[s] < (T)0));
+            const T mn = (s == arg1) ? min2 : min1;
+            m[s] = (T)sg * mn;
+        }
     }
 }
 

@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for cfg in "warp 0 2 5 1"; do
-  tag=$(echo $cfg | tr ' ' '_')
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:decode_warp_kernel -s 1 -c 1 -o gpurun_out/r2w_$tag -f python tools/warp_one.py $cfg > gpurun_out/r2w_ncu_$tag.log 2>&1
-  python tools/ncu_summary.py gpurun_out/r2w_$tag.ncu-rep > gpurun_out/r2w_$tag.txt 2>&1
-done
+( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 ) > gpurun_out/r2w_tests.txt
+cat gpurun_out/r2w_tests.txt
+for cfg in "warp 0 2 5 1" "warp 0 6 5 1" "warp 0 2 50 0" "warp 1 6 5 1"; do
+  python tools/warp_one.py $cfg 2>&1 | grep "dB iters"
+done > gpurun_out/r2w_times.txt
+cat gpurun_out/r2w_times.txt
