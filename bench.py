@@ -57,9 +57,10 @@ MUFU_PER_EDGE_ITER = 3                              # what the kernels execute: 
 SM_COUNT, XU_LANES = 148, 16
 # (the XU-pipe ceiling is measured in every run by ldpc535_probe_pipe_peak: 1 ex2 : 2 lg2 mix)
 # Min-sum (fp64, decode_warp_kernel<0,6,3>): warp instructions per codeword and iteration, counted in
-# the SASS of the iteration loop (tools/sass_count.py): 239 in all, 51 of them on the fp64 pipe.
-MINSUM_INSTR_PER_CW_ITER = 239
-MINSUM_FP64_PER_CW_ITER = 51
+# the SASS of the iteration loop (tools/sass_count.py): 164 in all, 30 of them on the fp64 pipe
+# (round 1: 239 / 51; the check update now uses prefix/suffix minima and sign bits, spa_math.cuh).
+MINSUM_INSTR_PER_CW_ITER = 164
+MINSUM_FP64_PER_CW_ITER = 30
 
 
 def config(n_cw, n_gpus):
@@ -385,9 +386,9 @@ def extra_configs(L, torch, np, c4, stream, sp, d_data, d_sym, n_cw, first_frame
                 row["roofline"] = {"bound": "sm_xu", "achieved": mufu / 1e12, "peak": mufu_peak / 1e12,
                                    "unit": "T MUFU/s", "frac": mufu / mufu_peak}
             else:
-                # min-sum runs in fp64; its loop is 239 warp instructions per codeword and iteration, so
+                # min-sum runs in fp64; its loop is 164 warp instructions per codeword and iteration, so
                 # the issue slots (1 warp instruction per clock and SM sub-partition) bound it before the
-                # fp64 pipe does (51 of the 239, 2 clocks each at the measured fp64 rate)
+                # fp64 pipe does (30 of the 164, 2 clocks each at the measured fp64 rate)
                 wi = MINSUM_INSTR_PER_CW_ITER * it_sum / (ms * 1e-3)
                 issue_peak = SM_COUNT * 4 * f_max
                 fp64_ops = MINSUM_FP64_PER_CW_ITER * 32 * it_sum / (ms * 1e-3)

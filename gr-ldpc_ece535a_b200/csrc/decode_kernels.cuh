@@ -213,34 +213,80 @@ decode_warp_kernel(const DecodeParams p)
     // warp (no registers held across the iterations): a warp that loaded and then used them sat out
     // the whole HBM latency once per codeword -- a fifth of all warp samples at 5 iterations (ncu,
     // profiles/r2c_*).
-    float *stage = reinterpret_cast<float *>(smem_w + sizeof(T) * (blockDim.x >> 5) * (kRows * 32)) + warp * 64;
-    auto fetch_window = [&](long long wq) {
-        if (wq < p.n_win) {
-            const long long offq = p.win_offset ? p.win_offset[wq] : wq * (long long)N;
-            if (offq >= 0 && offq + N <= p.n_sym) {
-                const float *g = p.sym_re ? p.sym_re + offq : reinterpret_cast<const float *>(p.sym + offq);
-                const int elt = p.sym_re ? 1 : 2;
-                if (lane < N) cp_async_f32(stage + lane, g + lane * elt);
-                if (lane + 32 < N) cp_async_f32(stage + lane + 32, g + (lane + 32) * elt);
-            }
+    //
+    // A warp takes BLOCKS of 32 consecutive windows (round 2; it used to take every warps_total-th
+    // one).  With early stop a codeword of the shipped code runs 1 to 5 iterations of ~120
+    // instructions and paid ~200 more for its window offset, bounds test, 64-bit addresses and three
+    // single-byte stores (half of all instructions at 6 dB).  Per block, lane j now loads offset and
+    // polarity of window j once (coalesced), keeps the results of window j, and the block's outputs
+    // leave as one coalesced store per array.
+    // Addresses are kept, not recomputed: the lane's word of the staging strip as a 32-bit shared
+    // address, the lane's symbol of the window to fetch next as a pointer that advances by one frame
+    // (aligned frames) or is rebuilt from the shuffled offset (search windows).  `opaque` keeps the
+    // compiler from rematerialising them from tid and the kernel parameters at every use (it did:
+    // ~50 instructions per prefetch).
+    auto opaque = [](uint32_t v) { asm volatile("" : "+r"(v)); return v; };
+    const uint32_t stage_a = opaque((uint32_t)__cvta_generic_to_shared(
+        reinterpret_cast<float *>(smem_w + sizeof(T) * (blockDim.x >> 5) * (kRows * 32)) + warp * 64 + lane));
+    const bool packed = p.sym_re != nullptr;                  // real parts only (4 bytes per symbol) or complex (8)
+    const char *gbase = packed ? reinterpret_cast<const char *>(p.sym_re) : reinterpret_cast<const char *>(p.sym);
+    const uint32_t esz = packed ? 4u : 8u;
+    auto fetch_at = [&](const char *g, bool okq) {           // g = this lane's first symbol of the window
+        if (okq) {
+            if (lane < N)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(stage_a), "l"(g) : "memory");
+            if (lane + 32 < N)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(stage_a + 128u), "l"(g + 32u * esz) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch_window((long long)blockIdx.x * (blockDim.x >> 5) + warp);
-    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w < p.n_win; w += warps_total) {
-        const long long off = p.win_offset ? p.win_offset[w] : w * (long long)N;
-        const float pol = p.polarity ? (float)p.polarity[w] : 1.f;
-        const bool ok = off >= 0 && off + N <= p.n_sym;
+    auto window_of = [&](long long wq, long long &offq, bool &okq) {
+        okq = wq < p.n_win;
+        offq = !okq ? 0 : p.win_offset ? p.win_offset[wq] : wq * (long long)N;
+        okq = okq && offq >= 0 && offq + N <= p.n_sym;
+    };
+    const long long n_blocks = (p.n_win + 31) >> 5;
+    const long long b0 = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const char *gnext;                                        // this lane's first symbol of the window fetched next
+    {
+        long long o; bool k;
+        window_of(b0 << 5, o, k);
+        gnext = gbase + (o + lane) * (long long)esz;
+        fetch_at(gnext, k);
+    }
+    for (long long blk = b0; blk < n_blocks; blk += warps_total) {
+      const long long w0 = blk << 5;
+      const int cnt = (int)min(32ll, p.n_win - w0);
+      long long off_l; bool ok_l;                       // of window w0 + lane
+      window_of(lane < cnt ? w0 + lane : p.n_win, off_l, ok_l);
+      const float pol_l = (p.polarity && lane < cnt) ? (float)p.polarity[w0 + lane] : 1.f;
+      const uint32_t okmask = __ballot_sync(0xffffffffu, ok_l);
+      uint32_t res_lo = 0, res_hi = 0, res_synd = 255, res_iters = 255;   // of window w0 + lane
+      for (int j = 0; j < cnt; j++) {
+        const long long w = w0 + j;
+        const bool ok = (okmask >> j) & 1u;
         constexpr float kIn = (METHOD == kMethodSpa) ? kSpaScale : 1.f;      // SPA works in units of ln 2
         constexpr float kOut = (METHOD == kMethodSpa) ? kSpaUnscale : 1.f;   // (message dumps only)
+        const float scale = p.polarity ? -kIn * __shfl_sync(0xffffffffu, pol_l, j) : -kIn;
         asm volatile("cp.async.wait_group 0;" ::: "memory");    // each lane reads back its own two words
         T r[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-            const int v = lane + 32 * t;
-            r[t] = (T)((ok && v < N) ? __fmul_rn(-pol * kIn, stage[v]) : 0.f);
+        {
+            float s0, s1;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s0) : "r"(stage_a));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s1) : "r"(stage_a + 128u));
+            r[0] = (T)((ok && lane < N) ? __fmul_rn(scale, s0) : 0.f);
+            r[1] = (T)((ok && lane + 32 < N) ? __fmul_rn(scale, s1) : 0.f);
         }
-        fetch_window(w + warps_total);
+        if (j + 1 < cnt) {
+            if (p.win_offset) gnext = gbase + (__shfl_sync(0xffffffffu, off_l, j + 1) + lane) * (long long)esz;
+            else gnext += (unsigned)N * esz;
+            fetch_at(gnext, (okmask >> (j + 1)) & 1u);
+        } else {
+            long long o; bool k;
+            window_of((blk + warps_total) << 5, o, k);
+            gnext = gbase + (o + lane) * (long long)esz;
+            fetch_at(gnext, k);
+        }
         float rk[2][DV];                               // r on a real edge of the bit, 0 on an unused slot
 #pragma unroll
         for (int t = 0; t < 2; t++)
@@ -278,16 +324,17 @@ decode_warp_kernel(const DecodeParams p)
             }
         } else {
             __syncwarp();
-            // M_ji = r_i on every edge (lib/ldpc_decoder_cb_impl.cc:489-496)
+            // M_ji = r_i on every edge (lib/ldpc_decoder_cb_impl.cc:489-496); unused slots write the dummy row
 #pragma unroll
-            for (int t = 0; t < 2; t++)
+            for (int t = 0; t < 2; t++) {
+                const T e0 = enc_msg<METHOD, T>(r[t]);
 #pragma unroll
-                for (int k = 0; k < DV; k++)
-                    if (k < vdeg[t]) {
-                        if (DEBUG && p.dbgS)
-                            p.dbgS[w * p.E + p.w_pos_edge[vpos[t][k]]] = (float)r[t] * kOut;
-                        st(vpos[t][k], enc_msg<METHOD, T>(r[t]));
-                    }
+                for (int k = 0; k < DV; k++) {
+                    if (DEBUG && p.dbgS && k < vdeg[t])
+                        p.dbgS[w * p.E + p.w_pos_edge[vpos[t][k]]] = (float)r[t] * kOut;
+                    st(vwr[t][k], e0);
+                }
+            }
             iters = p.max_iters;
             for (int h = 0; h < p.max_iters; h++) {
                 __syncwarp();
@@ -358,17 +405,28 @@ decode_warp_kernel(const DecodeParams p)
             }
         }
 
-        // ---- outputs ----
+        // ---- results of window j stay with lane j ----
         if (!ok) { hard0 = hard1 = 0; bad = 0xffffffffu; iters = 255; }
-        const unsigned long long hw = (unsigned long long)hard0 | ((unsigned long long)hard1 << 32);
-        if (lane < p.nbytes) {
-            const unsigned long long data = hw >> M;                 // bits M .. N-1
-            p.out_bytes[w * p.nbytes + lane] = pack_msb_first((uint32_t)(data >> (8 * lane)));
+        if (lane == j) {
+            const unsigned long long data = ((unsigned long long)hard0 | ((unsigned long long)hard1 << 32)) >> M;   // bits M .. N-1
+            // byte i of the output = bits 8 i .. 8 i + 7 of `data`, MSB first: reverse the bits of every byte
+            res_lo = __byte_perm(__brev((uint32_t)data), 0u, 0x0123);
+            res_hi = __byte_perm(__brev((uint32_t)(data >> 32)), 0u, 0x0123);
+            res_synd = (uint32_t)min(__popc(bad), p.thr + 1);
+            res_iters = (uint32_t)min(iters, 255);
         }
-        if (lane == 0) {
-            if (p.out_synd) p.out_synd[w] = (uint8_t)min(__popc(bad), p.thr + 1);
-            if (p.out_iters) p.out_iters[w] = (uint8_t)min(iters, 255);
-        }
+      }
+      // ---- outputs of the block: window w0 + lane ----
+      if (lane < cnt) {
+          if (p.nbytes == 4) {
+              reinterpret_cast<uint32_t *>(p.out_bytes)[w0 + lane] = res_lo;         // out_bytes is 4-byte aligned (ldpc535.h)
+          } else {
+              const unsigned long long rb = (unsigned long long)res_lo | ((unsigned long long)res_hi << 32);
+              for (int i = 0; i < p.nbytes; i++) p.out_bytes[(w0 + lane) * p.nbytes + i] = (uint8_t)(rb >> (8 * i));
+          }
+          if (p.out_synd) p.out_synd[w0 + lane] = (uint8_t)res_synd;
+          if (p.out_iters) p.out_iters[w0 + lane] = (uint8_t)res_iters;
+      }
     }
 }
 
