@@ -55,7 +55,8 @@ struct DecodeParams {
 // CTA runs until the slowest of its 256 codewords stops, a warp until its own codeword stops.  From
 // the iteration counts of a decoded sample: q_k = share of codewords that ran >= k iterations;
 //   lock step:  t0 + t1 * sum_k (1 - (1 - q_k)^256)      warp:  u0 + u1 * sum_k q_k
-// with the per-batch constants measured on B200 (us per 256 codewords per SM, profiles/r2_iter_sweep.txt).
+// with the per-batch constants measured on B200 (us per 256 codewords per SM; lock step: profiles/r2_iter_sweep.txt,
+// warp: fit to 35.6 / 70.4 / 104.1 Gbit/s at 4.73 / 2.19 / 1.27 mean iterations, profiles/r2_warp_layout.txt).
 __global__ void __launch_bounds__(256) pick_family_kernel(const uint8_t *iters, int n, int max_iters, int *select)
 {
     __shared__ int hist[256];
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) pick_family_kernel(const uint8_t *iters, 
             lock += 1.f - __powf(1.f - q, 256.f);
             ge -= hist[k];
         }
-        const float t_lock = 4.5f + 5.3f * lock, t_warp = 8.7f + 5.95f * mean;
+        const float t_lock = 4.5f + 5.3f * lock, t_warp = 3.4f + 6.46f * mean;
         *select = (t_lock < t_warp) ? 1 : 0;
     }
 }
@@ -228,6 +229,9 @@ decode_warp_kernel(const DecodeParams p)
     auto opaque = [](uint32_t v) { asm volatile("" : "+r"(v)); return v; };
     const uint32_t stage_a = opaque((uint32_t)__cvta_generic_to_shared(
         reinterpret_cast<float *>(smem_w + sizeof(T) * (blockDim.x >> 5) * (kRows * 32)) + warp * 64 + lane));
+    // result strip of the warp: 32 x (bytes lo, bytes hi, syndrome weight, iterations), behind the staging strips
+    const uint32_t res_a = opaque((uint32_t)__cvta_generic_to_shared(
+        smem_w + sizeof(T) * (blockDim.x >> 5) * (kRows * 32) + sizeof(float) * 64 * (blockDim.x >> 5) + 512 * warp));
     const bool packed = p.sym_re != nullptr;                  // real parts only (4 bytes per symbol) or complex (8)
     const char *gbase = packed ? reinterpret_cast<const char *>(p.sym_re) : reinterpret_cast<const char *>(p.sym);
     const uint32_t esz = packed ? 4u : 8u;
@@ -261,7 +265,6 @@ decode_warp_kernel(const DecodeParams p)
       window_of(lane < cnt ? w0 + lane : p.n_win, off_l, ok_l);
       const float pol_l = (p.polarity && lane < cnt) ? (float)p.polarity[w0 + lane] : 1.f;
       const uint32_t okmask = __ballot_sync(0xffffffffu, ok_l);
-      uint32_t res_lo = 0, res_hi = 0, res_synd = 255, res_iters = 255;   // of window w0 + lane
       for (int j = 0; j < cnt; j++) {
         const long long w = w0 + j;
         const bool ok = (okmask >> j) & 1u;
@@ -405,28 +408,34 @@ decode_warp_kernel(const DecodeParams p)
             }
         }
 
-        // ---- results of window j stay with lane j ----
+        // ---- results of window j: warp-uniform, parked in the warp's result strip by one lane ----
         if (!ok) { hard0 = hard1 = 0; bad = 0xffffffffu; iters = 255; }
-        if (lane == j) {
+        if (lane == 0) {
             const unsigned long long data = ((unsigned long long)hard0 | ((unsigned long long)hard1 << 32)) >> M;   // bits M .. N-1
             // byte i of the output = bits 8 i .. 8 i + 7 of `data`, MSB first: reverse the bits of every byte
-            res_lo = __byte_perm(__brev((uint32_t)data), 0u, 0x0123);
-            res_hi = __byte_perm(__brev((uint32_t)(data >> 32)), 0u, 0x0123);
-            res_synd = (uint32_t)min(__popc(bad), p.thr + 1);
-            res_iters = (uint32_t)min(iters, 255);
+            uint4 rv;
+            rv.x = __byte_perm(__brev((uint32_t)data), 0u, 0x0123);
+            rv.y = __byte_perm(__brev((uint32_t)(data >> 32)), 0u, 0x0123);
+            rv.z = (uint32_t)min(__popc(bad), p.thr + 1);
+            rv.w = (uint32_t)min(iters, 255);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(res_a + 16u * j), "r"(rv.x), "r"(rv.y), "r"(rv.z), "r"(rv.w) : "memory");
         }
       }
-      // ---- outputs of the block: window w0 + lane ----
+      // ---- outputs of the block: lane l stores window w0 + l ----
+      __syncwarp();
       if (lane < cnt) {
+          uint4 rv;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(res_a + 16u * lane));
           if (p.nbytes == 4) {
-              reinterpret_cast<uint32_t *>(p.out_bytes)[w0 + lane] = res_lo;         // out_bytes is 4-byte aligned (ldpc535.h)
+              reinterpret_cast<uint32_t *>(p.out_bytes)[w0 + lane] = rv.x;           // out_bytes is 4-byte aligned (ldpc535.h)
           } else {
-              const unsigned long long rb = (unsigned long long)res_lo | ((unsigned long long)res_hi << 32);
+              const unsigned long long rb = (unsigned long long)rv.x | ((unsigned long long)rv.y << 32);
               for (int i = 0; i < p.nbytes; i++) p.out_bytes[(w0 + lane) * p.nbytes + i] = (uint8_t)(rb >> (8 * i));
           }
-          if (p.out_synd) p.out_synd[w0 + lane] = (uint8_t)res_synd;
-          if (p.out_iters) p.out_iters[w0 + lane] = (uint8_t)res_iters;
+          if (p.out_synd) p.out_synd[w0 + lane] = (uint8_t)rv.z;
+          if (p.out_iters) p.out_iters[w0 + lane] = (uint8_t)rv.w;
       }
+      __syncwarp();
     }
 }
 

@@ -366,7 +366,7 @@ template <int METHOD, int DC, int DV, bool DBG>
 cudaError_t launch_warp(const ldpc535_code *c, const DecodeParams &p, cudaStream_t st)
 {
     const int wpb = kWarpKernelThreads / 32;
-    const size_t smem = sizeof(msg_t<METHOD>) * wpb * (DC + 3) * 32 + sizeof(float) * wpb * 64;   // + symbol staging
+    const size_t smem = sizeof(msg_t<METHOD>) * wpb * (DC + 3) * 32 + sizeof(float) * wpb * 64 + 512 * wpb;   // + symbol staging + results
     long long blocks = (p.n_win + wpb - 1) / wpb;
     auto kern = decode_warp_kernel<METHOD, DC, DV, DBG>;
     int per_sm = 8;                        // grid = the resident CTAs: one wave of persistent warps
