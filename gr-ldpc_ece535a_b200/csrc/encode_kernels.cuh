@@ -17,6 +17,7 @@ struct EncodeParams {
     int M, N, K, nbytes, kwords, mwords;
     const uint32_t *Pt;      // [K][mwords]  column masks (small codes)
     const uint32_t *Pw;      // [kwords][M]  word-major rows (generic)
+    int row_splits;          // generic kernel: a frame tile is shared by this many CTAs (parity rows and data half split), >= 1
 };
 
 // bytes (MSB first) -> word with bit k = data bit k
@@ -87,6 +88,9 @@ encode_small_kernel(const EncodeParams p)
 // feeds 4 * kEncRows LOP3s, so the integer pipe, not the shared-memory pipe, sets the pace:
 // M*K/32 AND-XOR words per frame (524 288 for the n = 8192 code) at 64 lanes/clk/SM bound this
 // kernel at ~36 % of the HBM write roofline.
+// Small batches (fewer tiles than twice the SMs) would leave most SMs idle for the 67 us a tile of
+// the n = 8192 code takes: p.row_splits CTAs then share a tile, each with M / row_splits parity
+// rows (a multiple of the 1024 rows a CTA pass covers) and its share of the data half.
 #ifndef ENC_TILE
 #define ENC_TILE 16
 #endif
@@ -112,8 +116,13 @@ encode_generic_kernel(const EncodeParams p)
     uint32_t *csm = enc_smem + (size_t)kEncTile * kw4;   // [kEncTile][mwords]
     const int tid = threadIdx.x, lane = tid & 31;
     const long long n_tiles = (p.n_frames + kEncTile - 1) / kEncTile;
+    const int RS = p.row_splits;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long unit = blockIdx.x; unit < n_tiles * RS; unit += gridDim.x) {
+        const long long tile = unit / RS;
+        const int rs = (int)(unit - tile * RS);
+        const int row_lo = (int)((long long)M * rs / RS), row_hi = (int)((long long)M * (rs + 1) / RS);   // parity rows of this CTA
+        const int dat_lo = M + (int)((long long)K * rs / RS) / 2 * 2, dat_hi = rs + 1 == RS ? N : M + (int)((long long)K * (rs + 1) / RS) / 2 * 2;
         const long long f0 = tile * kEncTile;
         const int nf = (int)min((long long)kEncTile, p.n_frames - f0);
         __syncthreads();
@@ -133,7 +142,7 @@ encode_generic_kernel(const EncodeParams p)
             dsm[idx] = word;
         }
         __syncthreads();
-        for (int jb = 0; jb < M; jb += kEncThreads * kEncRows) {
+        for (int jb = row_lo; jb < row_hi; jb += kEncThreads * kEncRows) {
             uint32_t acc[kEncRows][kEncTile];
 #pragma unroll
             for (int r = 0; r < kEncRows; r++)
@@ -146,7 +155,7 @@ encode_generic_kernel(const EncodeParams p)
                     const int j = jb + r * kEncThreads + tid;
 #pragma unroll
                     for (int q = 0; q < 4; q++)
-                        pw[r][q] = (j < M && w + q < p.kwords) ? __ldg(p.Pw + (size_t)(w + q) * M + j) : 0u;
+                        pw[r][q] = (j < row_hi && w + q < p.kwords) ? __ldg(p.Pw + (size_t)(w + q) * M + j) : 0u;
                 }
 #pragma unroll
                 for (int t = 0; t < kEncTile; t++) {
@@ -162,7 +171,7 @@ encode_generic_kernel(const EncodeParams p)
 #pragma unroll
                 for (int t = 0; t < kEncTile; t++) {
                     const uint32_t wd = __ballot_sync(0xffffffffu, __popc(acc[r][t]) & 1);
-                    if (lane == 0 && j < M) csm[(size_t)t * p.mwords + (j >> 5)] = wd;
+                    if (lane == 0 && j < row_hi) csm[(size_t)t * p.mwords + (j >> 5)] = wd;
                 }
             }
         }
@@ -173,6 +182,7 @@ encode_generic_kernel(const EncodeParams p)
             const uint32_t *dw = dsm + (size_t)t * kw4;
             if ((N & 1) == 0 && (M & 1) == 0) {
                 for (int i = 2 * tid; i < N; i += 2 * kEncThreads) {
+                    if (!((i >= row_lo && i < row_hi) || (i >= dat_lo && i < dat_hi))) continue;
                     uint32_t two;
                     if (i < M) two = (cw[i >> 5] >> (i & 31)) & 3u;
                     else { const int k = i - M; two = (dw[k >> 5] >> (k & 31)) & 3u; }
@@ -181,6 +191,7 @@ encode_generic_kernel(const EncodeParams p)
                 }
             } else {
                 for (int i = tid; i < N; i += kEncThreads) {
+                    if (!((i >= row_lo && i < row_hi) || (i >= dat_lo && i < dat_hi))) continue;
                     uint32_t bit;
                     if (i < M) bit = (cw[i >> 5] >> (i & 31)) & 1u;
                     else { const int k = i - M; bit = (dw[k >> 5] >> (k & 31)) & 1u; }

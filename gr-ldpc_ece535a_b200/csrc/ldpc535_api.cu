@@ -531,7 +531,7 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
     EncodeParams p;
     p.in = d_in; p.n_frames = (long long)n_frames; p.out = reinterpret_cast<float2 *>(d_out);
     p.M = t.M; p.N = t.N; p.K = t.K; p.nbytes = (t.K + 7) / 8; p.kwords = t.kwords; p.mwords = t.mwords;
-    p.Pt = c->d_Pt; p.Pw = c->d_Pw;
+    p.Pt = c->d_Pt; p.Pw = c->d_Pw; p.row_splits = 1;
     if (t.M <= 32 && t.K <= 32) {
         const long long warps = ((long long)n_frames + 31) / 32;
         const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)c->sm_count * 8);
@@ -614,7 +614,14 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
         cudaError_t e = cudaFuncSetAttribute(encode_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(LDPC535_ERR_CUDA, cudaGetErrorString(e));
         const long long tiles = ((long long)n_frames + kEncTile - 1) / kEncTile;
-        const int grid = (int)std::min<long long>(tiles, (long long)c->sm_count * 4);
+        // fewer tiles than SMs: several CTAs share one, each with a whole number of 1024-row passes (even row counts).
+        // Measured on the n = 8192 code: 500 frames 0.145 -> 0.054 ms, 1 000 frames 0.143 -> 0.086 ms; splitting beyond one
+        // CTA per SM only adds overhead (2 000 frames: 0.136 -> 0.162 ms with 4 CTAs per tile).
+        const int passes = std::max(1, t.M / (kEncThreads * kEncRows));
+        p.row_splits = 1;
+        if ((t.M % (kEncThreads * kEncRows)) == 0 && (t.K % 2) == 0)
+            while (p.row_splits * 2 <= passes && passes % (p.row_splits * 2) == 0 && tiles * p.row_splits * 2 <= (long long)c->sm_count) p.row_splits *= 2;
+        const int grid = (int)std::min<long long>(tiles * p.row_splits, (long long)c->sm_count * 4);
         encode_generic_kernel<<<grid, kEncThreads, smem, st>>>(p);
     }
     cudaError_t e = cudaGetLastError();
