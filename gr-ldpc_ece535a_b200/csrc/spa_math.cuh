@@ -106,8 +106,12 @@ __device__ __forceinline__ uint32_t check_node_spa(float (&m)[DC])
         if (s == 0) { ev = se[0]; od = so[0]; }
         else if (s == DC - 1) { ev = pe[s]; od = po[s]; }
         else {
-            ev = __fmaf_rn(po[s], so[s], __fmul_rn(pe[s], se[s]));
-            od = __fmaf_rn(po[s], se[s], __fmul_rn(pe[s], so[s]));
+            // pe[1] == 1 and se[DC - 2] == 1: x * 1 is x, exactly -- but the rn intrinsic keeps the multiply
+            // (3 FMULs by one per check in the SASS), so those products are written out as their value
+            const float pese = (s == 1) ? se[s] : (s == DC - 2) ? pe[s] : __fmul_rn(pe[s], se[s]);
+            const float peso = (s == 1) ? so[s] : __fmul_rn(pe[s], so[s]);
+            ev = __fmaf_rn(po[s], so[s], pese);
+            od = __fmaf_rn(po[s], se[s], peso);
         }
         const float mag = __fsub_rn(lg2_approx(ev), lg2_approx(od));
         // mag >= 0 (even >= odd): attach sign(all inputs) ^ sign(own input)
