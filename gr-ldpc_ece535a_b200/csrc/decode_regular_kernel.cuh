@@ -321,27 +321,38 @@ decode_regular_rt_kernel(const DecodeParams p, const uint16_t *__restrict__ var_
             // without it every bit paid the full shared-memory latency between its predecessor's stores
             // and its own loads (ncu source view, profiles/r2b: the first FADD after each load group held
             // 53 % of the variable phase's samples).  Distinct bits never share a message word.
-            float xn[DV] = {msg[a0(0)], msg[a1(0)], msg[a2(0)]};
-            float rn = rsm[tid];
-
+            // HARD = false: early stop off and not the last iteration -- nobody looks at the decisions: no total L,
+            // no comparison, no ballot, no tag (one instantiation of the loop for each case, picked per iteration).
+            auto var_phase = [&](auto hardc) {
+                constexpr bool HARD = decltype(hardc)::value;
+                float xn[DV] = {msg[a0(0)], msg[a1(0)], msg[a2(0)]};
+                float rn = rsm[tid];
 #pragma unroll
-            for (int q = 0; q < BQ; q++) {
-                const int i0 = (int)a0(q), i1 = (int)a1(q), i2 = (int)a2(q);
-                float x[DV] = {xn[0], xn[1], xn[2]};
-                const float rq = rn;
-                if (q + 1 < BQ) {            // (two bits ahead measured no better)
-                    xn[0] = msg[a0(q + 1)]; xn[1] = msg[a1(q + 1)]; xn[2] = msg[a2(q + 1)];
-                    rn = rsm[(q + 1) * NT + tid];
+                for (int q = 0; q < BQ; q++) {
+                    const int i0 = (int)a0(q), i1 = (int)a1(q), i2 = (int)a2(q);
+                    float x[DV] = {xn[0], xn[1], xn[2]};
+                    const float rq = rn;
+                    if (q + 1 < BQ) {            // (two bits ahead measured no better)
+                        xn[0] = msg[a0(q + 1)]; xn[1] = msg[a1(q + 1)]; xn[2] = msg[a2(q + 1)];
+                        rn = rsm[(q + 1) * NT + tid];
+                    }
+                    const float L = var_node_spa<DV>(x, DV, rq);
+                    if constexpr (HARD) {
+                        const bool b = (L <= 0.f);
+                        const uint32_t tagbit = b ? tagmask : 0u;
+                        msg[i0] = __uint_as_float(__float_as_uint(to_check_msg(x[0])) | tagbit);
+                        msg[i1] = __uint_as_float(__float_as_uint(to_check_msg(x[1])) | tagbit);
+                        msg[i2] = __uint_as_float(__float_as_uint(to_check_msg(x[2])) | tagbit);
+                        const uint32_t wd = __ballot_sync(0xffffffffu, b);
+                        if (lane == 0) hard[(q * NT + tid) >> 5] = wd;
+                    } else {
+                        msg[i0] = to_check_msg(x[0]);
+                        msg[i1] = to_check_msg(x[1]);
+                        msg[i2] = to_check_msg(x[2]);
+                    }
                 }
-                const float L = var_node_spa<DV>(x, DV, rq);
-                const bool b = (L <= 0.f);
-                const uint32_t tagbit = b ? tagmask : 0u;
-                msg[i0] = __uint_as_float(__float_as_uint(to_check_msg(x[0])) | tagbit);
-                msg[i1] = __uint_as_float(__float_as_uint(to_check_msg(x[1])) | tagbit);
-                msg[i2] = __uint_as_float(__float_as_uint(to_check_msg(x[2])) | tagbit);
-                const uint32_t wd = __ballot_sync(0xffffffffu, b);
-                if (lane == 0) hard[(q * NT + tid) >> 5] = wd;
-            }
+            };
+            if (tag || h + 1 == p.max_iters) var_phase(std::true_type{}); else var_phase(std::false_type{});
             __syncthreads();
         }
 
