@@ -31,6 +31,7 @@ struct Tables {
     int col_ptr[kN + 1];
     int edge_of_col[kE];    // CSR edge ids of a column, rows ascending
     unsigned row_lo[kM], row_hi[kM];
+    unsigned col_mask[kN];        // bit j = check j contains the bit (kM <= 32)
     bool ok;
 };
 
@@ -69,6 +70,11 @@ constexpr Tables make_tables()
     }
     t.row_ptr[kM] = e;
     if (e != kE) t.ok = false;
+    for (int c = 0; c < kN; c++) {
+        t.col_mask[c] = 0;
+        for (int j = 0; j < kM; j++)
+            if ((H[j] >> c) & 1ull) t.col_mask[c] |= 1u << j;
+    }
     int q = 0;
     for (int c = 0; c < kN; c++) {
         t.col_ptr[c] = q;
@@ -271,7 +277,10 @@ decode_c4_thread_kernel(const DecodeParams p)
         };
         // ---- Test (:519-532) fused with Step 2 (:540-553), then Finished? (:535-537) ----
         auto var_all = [&](int h) {
-            unsigned h0 = 0, h1 = 0;
+            // decisions: bits 32..63 are the output; the parity word `syn` (bit j = check j unsatisfied) is the XOR of
+            // the column masks of the bits decided 1 -- one predicated XOR per bit instead of a mask-and-popc per
+            // check over two packed words (324 -> ~160 instructions per iteration, same weight)
+            unsigned h1 = 0, syn = 0;
             static_for<kN>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 constexpr int a = kT.col_ptr[i];
@@ -293,18 +302,16 @@ decode_c4_thread_kernel(const DecodeParams p)
                     });
                 }
                 if (DEBUG && p.dbgL && live && !broke) p.dbgL[w * kN + i] = L * kSpaUnscale;
-                const unsigned bit = (L <= 0.f) ? 1u : 0u;          // :527
-                if constexpr (i < 32) h0 |= bit << i; else h1 |= bit << (i - 32);
+                constexpr unsigned cmask = kT.col_mask[i];
+                if (L <= 0.f) {                                     // :527
+                    syn ^= cmask;
+                    if constexpr (i >= 32) h1 |= 1u << (i - 32);
+                }
                 if constexpr (i % kVarGroup == kVarGroup - 1) group_sync();
             });
             // the syndrome is tested every iteration, the last included
             if (p.early_stop || h + 1 == p.max_iters) {
-                int cnt = 0;
-                static_for<kM>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr unsigned lo = kT.row_lo[j], hi = kT.row_hi[j];
-                    cnt += __popc((h0 & lo) ^ (h1 & hi)) & 1;
-                });
+                const int cnt = __popc(syn);
                 if (!broke) { out_h1 = h1; out_cnt = cnt; }
                 // A converged codeword stops here in the reference; its thread keeps pace with
                 // the CTA (barriers) but its outputs no longer change.
