@@ -22,3 +22,6 @@ ncu --set full --clock-control none --import-source on -k regex:decode_regular_r
     python tools/profile_kernels.py --which decode_block --c8k-codewords 8000 > gpurun_out/r2z_ncu_rt.log 2>&1
 python tools/ncu_summary.py gpurun_out/r2z_rt.ncu-rep > gpurun_out/r2z_rt.txt 2>&1
 cat gpurun_out/r2z_prof_plain.log gpurun_out/r2z_prof_c8k.log | grep -v "Exception\|Traceback\|File \|AttributeError"
+python tools/refill_sweep.py 4000000 2>&1 | grep "Eb/N0" > gpurun_out/r2z_early_stop_families.txt; cat gpurun_out/r2z_early_stop_families.txt
+python tools/enc_sweep.py --frames 500,2000,3072,8000,20000,200000,400000 --configs "ring=60" > gpurun_out/r2z_enc_sweep.txt 2>&1; cat gpurun_out/r2z_enc_sweep.txt
+for cfg in "warp 0 2 5 1" "warp 0 6 5 1" "warp 2 2 5 1"; do python tools/warp_one.py $cfg 2>&1 | grep "dB iters"; done > gpurun_out/r2z_warp_times.txt; cat gpurun_out/r2z_warp_times.txt
