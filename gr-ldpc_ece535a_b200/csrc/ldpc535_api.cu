@@ -536,8 +536,9 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
         const long long warps = ((long long)n_frames + 31) / 32;
         const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)c->sm_count * 8);
         encode_small_kernel<<<grid, 256, 0, st>>>(p);
-    // look-up encoder from ~3 k frames on (measured cross-over with the scan kernel: 2 k..4 k frames)
-    } else if (c->d_m4r && c->use_m4r && n_frames >= 3072 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
+    // look-up encoder from 2 048 frames on (measured: scan 0.081 / 0.151 / 0.284 ms at 1 000 / 2 000 / 3 000 frames,
+    // look-up 0.155 ms at 3 072 and 0.223 ms at 8 000: the curves cross at ~1 800 frames)
+    } else if (c->d_m4r && c->use_m4r && n_frames >= 2048 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
         // look-up encoder; batches are cut so that the kernel's 32-bit frame offsets hold
         const long long sms = c->sm_count, rbs = t.M / kM4rRows;

@@ -443,7 +443,7 @@ def test_c8k_lookup_encoder_equals_scan_encoder(c8k, monkeypatch, variant):
         monkeypatch.delenv("LDPC535_M4R_RING")
         monkeypatch.delenv("LDPC535_M4R_TPF", raising=False)
     rng = np.random.default_rng(18)
-    for n in (1, 257, 3071, 3072, 3073, 4100):             # the look-up kernel takes over at 3072 frames
+    for n in (1, 257, 2047, 2048, 2049, 3073, 4100):       # the look-up kernel takes over at 2048 frames
         data = rng.integers(0, 256, (n, c8k.nbytes)).astype(np.uint8)
         assert np.array_equal(look.encode(data), scan.encode(data)), n
     sms = L.device_info(0)["sm_count"]
