@@ -203,7 +203,9 @@ LDPC535_API int ldpc535_decode_debug(ldpc535_code *code, const float *sym, size_
  * Measurement knobs read from the environment at ldpc535_code_create* (results never change):
  * LDPC535_REGULAR_VARIANT=0 runs the (3,6)-regular n = 8192 code on the 1024-thread kernel instead
  * of the register-table one; LDPC535_ENCODER=generic keeps large codes on the AND/XOR scan encoder
- * instead of the table look-up one. */
+ * instead of the table look-up one; LDPC535_M4R_RING=40|60|42|62 picks the look-up encoder (free-running
+ * with a 4- / 6-slot ring, default 60; barrier kernel with a 4- / 6-slot ring), LDPC535_M4R_TPF=7|8 its
+ * frames per slot, LDPC535_M4R_TILE its frames per tile. */
 LDPC535_API int ldpc535_code_set_kernel(ldpc535_code *code, const char *kernel);
 
 /* How ldpc535_decode_batch moves host symbols to the device.  Pageable input is always staged

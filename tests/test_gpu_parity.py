@@ -672,6 +672,49 @@ def test_config3_full_size_round_trip(c4):
     assert bool((ob == (d ^ d2)).all()) and int(os_.max()) == 0
 
 
+def test_host_path_modes_agree_on_pinned_input():
+    """ldpc535_decode_batch on a PINNED caller buffer: the copy engine reading it as it is (0), the host team
+    packing the real parts first (1) and the measured choice between the two (2, the default) give identical
+    bytes, syndrome weights and iteration counts -- several 128 MiB chunks, so the measured mode has estimates
+    to act on -- and ldpc535_code_host_stats accounts for every chunk and every PCIe byte."""
+    import ctypes as C
+    from ldpc_ece535a import _abi
+    code = L.Code(None, device=0)
+    n = 600_000                                    # 307 MB of complex symbols: 3 chunks
+    rng = np.random.default_rng(77)
+    data = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    sym = code.encode(data)
+    sym.real += rng.standard_normal(sym.shape, dtype=np.float32) * np.float32(0.8)
+    p = C.c_void_p()
+    _abi.check(_abi.lib().ldpc535_host_alloc(sym.nbytes, C.byref(p)), "host_alloc")
+    try:
+        pinned = np.frombuffer((C.c_uint8 * sym.nbytes).from_address(p.value), dtype=np.complex64).reshape(sym.shape)
+        pinned[...] = sym
+        assert code.host_path()["pack_pinned"] == 2
+        res = {}
+        for mode in (0, 1, 2, 2):
+            code.set_host_path(mode, 0)
+            s0 = code.host_stats()
+            res[mode] = code.decode(pinned, method=1, max_iters=5, early_stop=True)
+            s1 = code.host_stats()
+            packed, raw = s1["chunks_packed"] - s0["chunks_packed"], s1["chunks_raw"] - s0["chunks_raw"]
+            assert packed + raw >= 3
+            assert s1["h2d_bytes"] - s0["h2d_bytes"] in range(n * 64 * 4, n * 64 * 8 + 1)
+            if mode == 0:
+                assert packed == 0 and s1["h2d_bytes"] - s0["h2d_bytes"] == n * 64 * 8
+            if mode == 1:
+                assert raw == 0 and s1["h2d_bytes"] - s0["h2d_bytes"] == n * 64 * 4
+        for mode in (1, 2):
+            for x, y in zip(res[0], res[mode]):
+                assert np.array_equal(x, y), mode
+        want = code.decode(sym, method=1, max_iters=5, early_stop=True)       # pageable input: always packed
+        for x, y in zip(res[0], want):
+            assert np.array_equal(x, y)
+    finally:
+        _abi.lib().ldpc535_host_free(p)
+        code.close()
+
+
 @pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0]])
 def test_pool_shards_and_gathers(c4, devices):
     """ldpc535_pool: contiguous shards over several handles (here on one GPU; on a multi-GPU box
