@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python tools/refill_sweep.py 4000000 2>&1 | grep "Eb/N0" > gpurun_out/r2n_early_stop_families.txt
-cat gpurun_out/r2n_early_stop_families.txt
+( timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_build.py tests/test_gpu_blocks.py -m gpu -x -q 2>&1 | tail -3 ) > gpurun_out/r2w_tests.txt; cat gpurun_out/r2w_tests.txt
+for cfg in "warp 0 2 5 1" "warp 0 6 5 1" "warp 0 2 50 0"; do python tools/warp_one.py $cfg 2>&1 | grep "dB iters"; done
