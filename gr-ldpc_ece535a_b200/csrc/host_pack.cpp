@@ -4,6 +4,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
@@ -62,38 +63,60 @@ int default_pack_threads()
     return (int)std::max(1u, std::min(32u, hc));
 }
 
+// The team: workers take blocks of 64 Ki symbols from a shared counter (no thread finishes long
+// after the others), spin for ~100 us between jobs before they sleep on the condition variable --
+// decode_batch packs a 128 MiB chunk every ~1.8 ms, and a sleeping worker's wake-up (tens of
+// microseconds, 38 times per 5.12 GB) was part of every chunk -- and the caller spins the same way
+// for the last block to finish.
 struct PackPool::Impl {
+    static constexpr size_t kBlock = (size_t)1 << 16;       // symbols per block
+    static constexpr int kSpin = 4000;                       // pause iterations before sleeping (~50-150 us)
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
     std::vector<std::thread> workers;
-    // one job at a time: parts [1, parts) belong to the workers, part 0 to the caller
+    // one job at a time, published by `generation` (release) and read after it (acquire)
     const float *src = nullptr;
     float *dst = nullptr;
-    size_t n = 0, per = 0;
+    size_t n = 0;
     int parts = 0;
-    unsigned long generation = 0;
-    int pending = 0;
-    bool stop = false;
+    std::atomic<size_t> next{0};                             // next block to be taken
+    std::atomic<unsigned long> generation{0};
+    std::atomic<int> pending{0};                             // workers still on the current job
+    std::atomic<bool> stop{false};
 
-    void run_part(int k) const
+    void run_blocks()
     {
-        const size_t lo = std::min(n, per * (size_t)k), hi = std::min(n, per * (size_t)(k + 1));
-        if (hi > lo) g_pack(src + 2 * lo, dst + lo, hi - lo);
+        for (;;) {
+            const size_t lo = next.fetch_add(kBlock, std::memory_order_relaxed);
+            if (lo >= n) return;
+            const size_t hi = std::min(n, lo + kBlock);
+            g_pack(src + 2 * lo, dst + lo, hi - lo);
+        }
     }
 
     void worker(int id)
     {
         unsigned long seen = 0;
-        std::unique_lock<std::mutex> lk(mu);
         for (;;) {
-            cv_work.wait(lk, [&] { return stop || generation != seen; });
-            if (stop) return;
-            seen = generation;
+            unsigned long g = seen;
+            for (int i = 0; i < kSpin; i++) {
+                g = generation.load(std::memory_order_acquire);
+                if (g != seen || stop.load(std::memory_order_relaxed)) break;
+                _mm_pause();
+            }
+            if (g == seen && !stop.load(std::memory_order_relaxed)) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop.load() || generation.load(std::memory_order_acquire) != seen; });
+                g = generation.load(std::memory_order_acquire);
+            }
+            if (stop.load()) return;
+            seen = g;
             if (id < parts) {
-                lk.unlock();
-                run_part(id);
-                lk.lock();
-                if (--pending == 0) cv_done.notify_one();
+                run_blocks();
+                if (pending.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    cv_done.notify_one();
+                }
             }
         }
     }
@@ -108,7 +131,7 @@ PackPool::~PackPool()
 {
     {
         std::lock_guard<std::mutex> lk(impl_->mu);
-        impl_->stop = true;
+        impl_->stop.store(true);
     }
     impl_->cv_work.notify_all();
     for (auto &t : impl_->workers) t.join();
@@ -124,15 +147,19 @@ void PackPool::pack(const float *src, float *dst, size_t n)
     {
         std::lock_guard<std::mutex> lk(s.mu);
         s.src = src; s.dst = dst; s.n = n;
-        s.per = (((n + parts - 1) / parts) + 15) & ~(size_t)15;
         s.parts = parts;
-        s.pending = parts - 1;
-        s.generation++;
+        s.next.store(0, std::memory_order_relaxed);
+        s.pending.store(parts - 1, std::memory_order_relaxed);
+        s.generation.fetch_add(1, std::memory_order_release);
     }
     s.cv_work.notify_all();
-    s.run_part(0);
+    s.run_blocks();
+    for (int i = 0; i < Impl::kSpin; i++) {
+        if (s.pending.load(std::memory_order_acquire) == 0) return;
+        _mm_pause();
+    }
     std::unique_lock<std::mutex> lk(s.mu);
-    s.cv_done.wait(lk, [&] { return s.pending == 0; });
+    s.cv_done.wait(lk, [&] { return s.pending.load(std::memory_order_acquire) == 0; });
 }
 
 }  // namespace ldpc535
