@@ -120,11 +120,15 @@ constexpr int kCtasPerSm = C4_CTAS;
 // twelve warps streaming it independently stall on instruction fetch (ncu: no_instruction was
 // the top stall).  A CTA barrier every few nodes keeps all warps of the SM within one
 // cache-resident window of the code, so each line is fetched once per SM per pass.
+// Round 1's body (2 990 instructions per iteration) was fastest with a barrier every 8 checks / 16
+// bits; the shorter round-2 body (2 846) with one after the 32 checks and one every 32 bits (A/B on
+// one box, ms per 2 M codewords at 50 iterations: 8/16 12.97, 16/32 12.82, 11/22 12.73, 32/32 12.71,
+// 32/22 12.92, 32/16 12.96, 16/64 12.93, 4/8 13.39).
 #ifndef C4_CHK_GROUP
-#define C4_CHK_GROUP 8
+#define C4_CHK_GROUP 32
 #endif
 #ifndef C4_VAR_GROUP
-#define C4_VAR_GROUP 16
+#define C4_VAR_GROUP 32
 #endif
 constexpr int kChkGroup = C4_CHK_GROUP;     // checks between barriers
 constexpr int kVarGroup = C4_VAR_GROUP;     // variables between barriers
