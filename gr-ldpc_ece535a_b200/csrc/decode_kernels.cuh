@@ -55,8 +55,8 @@ struct DecodeParams {
 // CTA runs until the slowest of its 256 codewords stops, a warp until its own codeword stops.  From
 // the iteration counts of a decoded sample: q_k = share of codewords that ran >= k iterations;
 //   lock step:  t0 + t1 * sum_k (1 - (1 - q_k)^256)      warp:  u0 + u1 * sum_k q_k
-// with the per-batch constants measured on B200 (us per 256 codewords per SM; lock step: 12.98 ms per 2 M codewords at
-// 50 iterations and 1.48 ms at 5, profiles/r2_node_rate2.txt;
+// with the per-batch constants measured on B200 (us per 256 codewords per SM; lock step: 12.71 ms per 2 M codewords at
+// 50 iterations and 1.455 ms at 5, profiles/r2_node_rate2.txt;
 // warp: fit to 35.6 / 70.4 / 104.1 Gbit/s at 4.73 / 2.19 / 1.27 mean iterations, profiles/r2_warp_layout.txt).
 __global__ void __launch_bounds__(256) pick_family_kernel(const uint8_t *iters, int n, int max_iters, int *select)
 {
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) pick_family_kernel(const uint8_t *iters, 
             lock += 1.f - __powf(1.f - q, 256.f);
             ge -= hist[k];
         }
-        const float t_lock = 3.6f + 4.85f * lock, t_warp = 3.4f + 6.46f * mean;
+        const float t_lock = 3.6f + 4.77f * lock, t_warp = 3.4f + 6.46f * mean;
         *select = (t_lock < t_warp) ? 1 : 0;
     }
 }
