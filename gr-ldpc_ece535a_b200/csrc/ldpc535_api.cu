@@ -24,6 +24,7 @@
 #include "decode_hard_kernel.cuh"
 #include "encode_kernels.cuh"
 #include "encode_m4r_kernel.cuh"
+#include "encode_m4r_tiles.h"
 #include "host_pack.h"
 #include "synth_kernels.cuh"
 #include "ldpc535_default_code.h"
@@ -553,21 +554,11 @@ int launch_encode(ldpc535_code *c, const uint8_t *d_in, size_t n_frames, float *
             const bool fr = c->m4r_ring == 40 || c->m4r_ring == 60;
             const int tpf = fr ? c->m4r_tpf : 8;
             const long long slots = fr ? kM4rFrSlots : kM4rSlots, cap = slots * tpf;
-            long long tiles = (nf + cap - 1) / cap;
-            if (c->m4r_tile > 0) {
-                tiles = (nf + std::min<long long>(cap, c->m4r_tile) - 1) / std::min<long long>(cap, c->m4r_tile);
-            } else {
-                double best = 1e300;
-                for (long long nt = tiles, last = tiles + 2 * sms; nt <= last && nt <= nf; nt++) {
-                    const long long fr_t = (nf + nt - 1) / nt;
-                    const double cost = (double)((nt * rbs + sms - 1) / sms) * (2.85 + (double)fr_t / slots);
-                    if (cost < best - 1e-9) { best = cost; tiles = nt; }
-                }
-            }
+            const M4rTiling tiling = m4r_choose_tiling(nf, rbs, sms, slots, cap, c->m4r_tile);
             M4rRun run;
-            run.tile_frames = (uint32_t)std::min<long long>(cap, (nf + tiles - 1) / tiles);
+            run.tile_frames = (uint32_t)tiling.tile_frames;
             run.flags = c->m4r_flags;
-            const long long units = ((nf + run.tile_frames - 1) / run.tile_frames) * rbs;
+            const long long units = tiling.units;
             const int grid = (int)std::min<long long>(units, sms);
             cudaError_t e;
             if (fr) {
